@@ -1,0 +1,61 @@
+"""Build liblora_b200.so (the CUDA library + C ABI) in-tree with nvcc for sm_100a.
+
+The built .so sits next to this file so that it travels with the repository snapshot to the
+GPU box (the JIT cache under ~/.cache would not)."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+ROOT = PKG.parent
+CSRC = PKG / "csrc"
+LIB = PKG / "liblora_b200.so"
+HOST_EMUL = ROOT / "build" / "host_emul.so"
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "-shared", "--use_fast_math=false"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and Path(cand).exists():
+            return cand
+    raise RuntimeError("nvcc not found: cannot build liblora_b200.so")
+
+
+def _stale(target: Path, sources) -> bool:
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(Path(s).stat().st_mtime > t for s in sources)
+
+
+def _sources():
+    return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "lora_b200.h"]
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if force or _stale(LIB, _sources()):
+        flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+        cmd = [_nvcc(), *flags, "-o", str(LIB), str(CSRC / "lora_b200.cu")]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return LIB
+
+
+def build_host_emul(force: bool = False) -> Path:
+    """CPU build of the kernels' __host__ __device__ phase functions (non-GPU tests only)."""
+    if force or _stale(HOST_EMUL, _sources()):
+        HOST_EMUL.parent.mkdir(exist_ok=True)
+        cmd = [_nvcc(), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+               "-shared", "-o", str(HOST_EMUL), str(CSRC / "host_emul.cu")]
+        subprocess.run(cmd, check=True)
+    return HOST_EMUL
+
+
+if __name__ == "__main__":
+    print(build(verbose=True))

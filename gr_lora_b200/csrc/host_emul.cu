@@ -1,0 +1,38 @@
+// host_emul.cu -- CPU entry points for the __host__ __device__ phase functions (tests only).
+// Lets the non-GPU test-suite run the kernels' index arithmetic, twiddles and integer chain
+// on the host and compare them with the oracle.  Not part of liblora_b200.so.
+#include "k1_fft.cuh"
+#include "int_chain.cuh"
+
+extern "C" {
+
+int lb_k1_emulate(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw,
+                  uint32_t *bins, float *mags) {
+    lb::K1Args a{x, chirp, tw, n_symbols};
+    switch (sf) {
+    case 7: lb::k1_emulate<7>(a, bins, mags); break;
+    case 8: lb::k1_emulate<8>(a, bins, mags); break;
+    case 9: lb::k1_emulate<9>(a, bins, mags); break;
+    case 10: lb::k1_emulate<10>(a, bins, mags); break;
+    case 11: lb::k1_emulate<11>(a, bins, mags); break;
+    case 12: lb::k1_emulate<12>(a, bins, mags); break;
+    default: return -1;
+    }
+    return 0;
+}
+
+uint32_t lb_emul_decode(const uint8_t *cw, uint32_t n_cw, int is_header, uint32_t cr, uint8_t *out, uint32_t cap) {
+    uint32_t n = lb::decode_len_bytes(lb::decode_len_words(n_cw, is_header), cr);
+    if (n > cap) n = cap;
+    for (uint32_t i = 0; i < n; i++) out[i] = lb::decode_byte(cw, n_cw, is_header, cr, i);
+    return n;
+}
+void lb_emul_deinterleave(const uint32_t *words, uint32_t n_words, uint32_t ppm, uint8_t *out) { lb::deinterleave_block(words, n_words, ppm, out); }
+uint32_t lb_emul_reduce_bin(uint32_t bin, uint32_t n_hdr) { return lb::reduce_bin(bin, n_hdr); }
+uint32_t lb_emul_gray(uint32_t bin) { return lb::gray_encode(bin); }
+uint8_t lb_emul_hamming84_decode(uint8_t cw) { return lb::hamming84_decode(cw); }
+uint8_t lb_emul_hamming84_encode(uint8_t v) { return lb::hamming84_encode(v); }
+uint8_t lb_emul_deshuffle(uint8_t v) { return lb::deshuffle_byte(v); }
+int32_t lb_emul_payload_symbols(uint32_t len, uint32_t cr, uint32_t sf, int rr) { return lb::payload_symbols(len, cr, sf, rr); }
+
+}

@@ -1,0 +1,647 @@
+// lora_b200.cu -- C-ABI implementation of liblora_b200.so (see include/lora_b200.h).
+// Host side: parameter derivation and table construction exactly as the reference's
+// constructor does them (lib/decoder_impl.cc:49-122,141-175), device memory, streams,
+// pinned staging and kernel launches.  There is no CPU compute path in this file.
+#include "../../include/lora_b200.h"
+#include "k1_fft.cuh"
+#include "rx_stream.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace lb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) return fail(LORA_B200_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct Tables {          // offsets (bytes) inside the device blob, see lora_b200_tables_bytes
+    size_t down, up, down_ifreq, up_ifreq, up_ifreq_v, tw, total;
+};
+
+}  // namespace
+
+struct lora_b200_decoder {
+    lora_b200_config cfg;
+    // derived, decoder_impl.cc:69-91
+    uint32_t samples_per_second, sps, n_bins, n_bins_hdr, decim, delay_after_sync;
+    double dt, symbols_per_second, bits_per_second, bits_per_symbol;
+    bool k1_ok;                           // fs/bw == 8 and SF7..12: FFT kernels usable
+    int device, n_sms;
+    Tables toff;
+    uint8_t *d_tables = nullptr;
+    std::vector<uint8_t> h_tables;
+    float down_ifreq_avg = 0.f, down_ifreq_sd = 0.f;
+    // K1
+    unsigned long long *d_packed = nullptr;
+    size_t packed_cap = 0;
+    float *d_k2_scratch = nullptr;
+    int k2_grid = 0;
+    // e2e host path
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};
+    cudaEvent_t copy_events[2] = {nullptr, nullptr};
+    void *d_chunk[2] = {nullptr, nullptr};
+    void *h_chunk[2] = {nullptr, nullptr};
+    uint32_t *d_chunk_bins[2] = {nullptr, nullptr};
+    float *d_chunk_mags[2] = {nullptr, nullptr};
+    size_t chunk_symbols = 0;
+    // stream path
+    cudaStream_t rx_stream = nullptr;
+    RxStreamState *d_states = nullptr;
+    float *d_scratch = nullptr;
+    unsigned long long *d_consumed = nullptr;
+    RxFrameRec *d_frames = nullptr;
+    RxFrameOut *d_frames_out = nullptr;
+    uint32_t *d_n_frames = nullptr;
+    uint32_t frame_cap = 0;
+    lora_b200_step *d_trace = nullptr;
+    uint32_t *d_trace_n = nullptr;
+    float2 *d_stage = nullptr;            // [n_streams][max_items]
+    float2 *h_stage = nullptr;            // pinned, same shape
+    std::vector<unsigned long long> h_consumed;
+    std::vector<RxFrameOut> h_frames;
+    std::vector<std::string> stdout_last;
+    std::vector<int> h_state;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+// ---- table construction (host, float phase + sincosf exactly like gr_expj) ---------------
+void ifreq_host(const float2 *in, float *out, uint32_t window) {     // decoder_impl.cc:224-244
+    for (uint32_t i = 1u; i < window; i++) {
+        const float p1 = atan2f(in[i - 1].y, in[i - 1].x);
+        float p2 = atan2f(in[i].y, in[i].x);
+        while ((p2 - p1) > M_PI) p2 = (float)(p2 - 2.0f * M_PI);
+        while ((p2 - p1) < -M_PI) p2 = (float)(p2 + 2.0f * M_PI);
+        out[i - 1] = p2 - p1;
+    }
+    out[window - 1] = out[window - 2];
+}
+
+void build_tables(lora_b200_decoder *d) {
+    const uint32_t sps = d->sps;
+    Tables &t = d->toff;
+    size_t o = 0;
+    t.down = o; o += sizeof(float2) * sps;
+    t.up = o; o += sizeof(float2) * sps;
+    t.down_ifreq = o; o += sizeof(float) * sps;
+    t.up_ifreq = o; o += sizeof(float) * sps;
+    t.up_ifreq_v = o; o += sizeof(float) * sps * 3;
+    t.tw = o; o += sizeof(float2) * sps;
+    t.total = (o + 255) & ~(size_t)255;
+    d->h_tables.assign(t.total, 0);
+    float2 *down = (float2 *)(d->h_tables.data() + t.down);
+    float2 *up = (float2 *)(d->h_tables.data() + t.up);
+    float *dif = (float *)(d->h_tables.data() + t.down_ifreq);
+    float *uif = (float *)(d->h_tables.data() + t.up_ifreq);
+    float *uifv = (float *)(d->h_tables.data() + t.up_ifreq_v);
+    float2 *tw = (float2 *)(d->h_tables.data() + t.tw);
+
+    const double T = -0.5 * d->cfg.bandwidth * d->symbols_per_second;    // :149
+    const double f0 = d->cfg.bandwidth / 2.0;                            // :150
+    const double pre_dir = 2.0 * M_PI;
+    for (uint32_t i = 0; i < sps; i++) {
+        const double tt = d->dt * i;                                     // :158
+        const float ph_d = (float)(pre_dir * tt * (f0 + T * tt));        // gr_expj(float), :159
+        const float ph_u = (float)(pre_dir * tt * (f0 + T * tt) * -1.0f);    // :160
+        const float cd = cosf(ph_d), sd = sinf(ph_d), cu = cosf(ph_u), su = sinf(ph_u);
+        down[i] = make_float2(cd - sd, sd + cd);                         // (1+1j) * e^{j phase}
+        up[i] = make_float2(cu - su, su + cu);
+    }
+    ifreq_host(down, dif, sps);                                          // :164
+    ifreq_host(up, uif, sps);                                            // :165
+    std::vector<float2> tmp(3 * (size_t)sps);
+    for (int k = 0; k < 3; k++) memcpy(tmp.data() + (size_t)k * sps, up, sizeof(float2) * sps);   // :171-173
+    ifreq_host(tmp.data(), uifv, 3 * sps);                               // :174
+    for (uint32_t j = 0; j < sps; j++) {                                 // forward DFT twiddles W_sps^j
+        const double a = -2.0 * M_PI * (double)j / (double)sps;
+        tw[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+}
+
+void table_stats(lora_b200_decoder *d) {     // chirp_avg and stddev of the ideal down-chirp, :287-289
+    const float *dif = (const float *)(d->h_tables.data() + d->toff.down_ifreq);
+    const uint32_t to_idx = d->sps - 1u;
+    float acc = 0.0f;
+    for (uint32_t i = 0; i < to_idx; i++) acc += dif[i];
+    const float avg = acc / (float)to_idx;
+    float var = 0.0f;
+    for (uint32_t i = 0; i < to_idx; i++) { const float t = dif[i] - avg; var += t * t; }
+    var /= (float)to_idx;
+    d->down_ifreq_avg = avg;
+    d->down_ifreq_sd = sqrtf(var);
+}
+
+template <typename T>
+const T *tab(const lora_b200_decoder *d, size_t off) { return (const T *)(d->d_tables + off); }
+
+// ---- K1 launch -----------------------------------------------------------------------------
+template <int SF>
+int launch_k1(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    using C = K1Cfg<SF>;
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(float2) * C::SMEM_ELEMS;
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_fft_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    const size_t n_work = ((n_symbols + C::G - 1) / C::G) * C::S;
+    const int grid = (int)std::min<size_t>(n_work, (size_t)d->n_sms * 2);
+    if (C::S > 1) {
+        if (d->packed_cap < n_symbols) {
+            if (d->d_packed) cudaFree(d->d_packed);
+            d->d_packed = nullptr; d->packed_cap = 0;
+            CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
+            d->packed_cap = n_symbols;
+        }
+        CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    }
+    k1_fft_kernel<SF><<<grid, K1_THREADS, smem, st>>>(a, bins, mags, d->d_packed);
+    d->launches++;
+    if (C::S > 1) {
+        k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+        d->launches++;
+    }
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins, float *mags, cudaStream_t st) {
+    if (!d->k1_ok) return fail(LORA_B200_EUNSUPPORTED, "FFT demodulator needs samp_rate/bandwidth == 8 and SF7..SF12");
+    if (n == 0) return LORA_B200_OK;
+    switch (d->cfg.sf) {
+    case 7: return launch_k1<7>(d, iq, n, bins, mags, st);
+    case 8: return launch_k1<8>(d, iq, n, bins, mags, st);
+    case 9: return launch_k1<9>(d, iq, n, bins, mags, st);
+    case 10: return launch_k1<10>(d, iq, n, bins, mags, st);
+    case 11: return launch_k1<11>(d, iq, n, bins, mags, st);
+    case 12: return launch_k1<12>(d, iq, n, bins, mags, st);
+    }
+    return fail(LORA_B200_EUNSUPPORTED, "unsupported SF %u", d->cfg.sf);
+}
+
+// ---- stream-path launch -----------------------------------------------------------------------
+template <int SF, bool FFT>
+int launch_rx_t(lora_b200_decoder *d, const RxParams &p, int grid, cudaStream_t st) {
+    size_t smem = 0;
+    if (FFT) {
+        smem = sizeof(float2) * K1Cfg<SF>::SMEM_ELEMS;
+        static bool attr_set[64] = {};
+        if (!attr_set[d->device & 63]) {
+            CU(cudaFuncSetAttribute(rx_stream_kernel<SF, FFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[d->device & 63] = true;
+        }
+    }
+    rx_stream_kernel<SF, FFT><<<grid, RX_THREADS, smem, st>>>(p);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+int launch_rx(lora_b200_decoder *d, const RxParams &p, int grid, cudaStream_t st) {
+    const bool fft = d->cfg.demod == LORA_B200_DEMOD_FFT;
+    if (!fft) return launch_rx_t<7, false>(d, p, grid, st);       // SF is a run-time value on the gradient path
+    switch (d->cfg.sf) {
+    case 7: return launch_rx_t<7, true>(d, p, grid, st);
+    case 8: return launch_rx_t<8, true>(d, p, grid, st);
+    case 9: return launch_rx_t<9, true>(d, p, grid, st);
+    case 10: return launch_rx_t<10, true>(d, p, grid, st);
+    case 11: return launch_rx_t<11, true>(d, p, grid, st);
+    case 12: return launch_rx_t<12, true>(d, p, grid, st);
+    }
+    return fail(LORA_B200_EUNSUPPORTED, "unsupported SF %u", d->cfg.sf);
+}
+
+void append_hex(std::string &s, const uint8_t *v, size_t n, bool endline, bool ascii) {   // print_vector_hex, utilities.h:351-368
+    char b[8];
+    std::string asc;
+    for (size_t i = 0; i < n; i++) {
+        snprintf(b, sizeof b, " %02x", v[i]);
+        s += b;
+        if (v[i] >= ' ' && v[i] <= '~') asc.push_back((char)v[i]);
+    }
+    if (ascii) s += " (" + asc + ")";
+    if (endline) s += "\n";
+}
+
+int run_rx(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t n_items, uint32_t stream_base,
+           uint32_t n_launch, size_t *consumed, lora_b200_frame_cb cb, void *user) {
+    cudaStream_t st = d->rx_stream;
+    CU(cudaMemsetAsync(d->d_n_frames, 0, sizeof(uint32_t), st));
+    RxParams p;
+    memset(&p, 0, sizeof p);
+    p.iq = d_iq; p.stride_items = stride_items; p.n_items = n_items; p.stream_base = stream_base;
+    p.down = tab<float2>(d, d->toff.down);
+    p.down_ifreq = tab<float>(d, d->toff.down_ifreq);
+    p.up_ifreq = tab<float>(d, d->toff.up_ifreq);
+    p.up_ifreq_v = tab<float>(d, d->toff.up_ifreq_v);
+    p.tw = tab<float2>(d, d->toff.tw);
+    p.down_ifreq_avg = d->down_ifreq_avg; p.down_ifreq_sd = d->down_ifreq_sd;
+    p.sps = d->sps; p.n_bins = d->n_bins; p.n_bins_hdr = d->n_bins_hdr; p.decim = d->decim; p.sf = d->cfg.sf;
+    p.implicit = d->cfg.implicit; p.reduced_rate = d->cfg.reduced_rate; p.enable_fine_sync = !d->cfg.disable_drift_correction;
+    p.states = d->d_states; p.scratch = d->d_scratch; p.consumed = d->d_consumed;
+    p.frames = d->d_frames; p.n_frames = d->d_n_frames; p.frame_cap = d->frame_cap;
+    p.max_frames_per_stream = d->cfg.max_frames_per_call;
+    p.trace = d->d_trace; p.trace_cap = d->cfg.trace_capacity; p.trace_n = d->d_trace_n;
+    int rc = launch_rx(d, p, (int)n_launch, st);
+    if (rc) return rc;
+    const int k8_grid = (int)std::min<uint32_t>(d->frame_cap, (uint32_t)d->n_sms * 4u);
+    k8_frames_kernel<<<k8_grid, 128, 0, st>>>(d->d_frames, d->d_n_frames, d->frame_cap, d->d_frames_out);
+    d->launches++;
+    CU(cudaGetLastError());
+    uint32_t n_frames = 0;
+    CU(cudaMemcpyAsync(&n_frames, d->d_n_frames, sizeof n_frames, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(d->h_consumed.data() + stream_base, d->d_consumed + stream_base,
+                       sizeof(unsigned long long) * n_launch, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_frames > d->frame_cap) n_frames = d->frame_cap;
+    d->h_frames.resize(n_frames);
+    if (n_frames) {
+        CU(cudaMemcpyAsync(d->h_frames.data(), d->d_frames_out, sizeof(RxFrameOut) * n_frames, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    for (uint32_t s = 0; s < n_launch; s++) {
+        consumed[s] = (size_t)d->h_consumed[stream_base + s];
+        d->stdout_last[stream_base + s].clear();
+    }
+    // queue order is arrival order across streams; deliver per stream in sequence order
+    std::vector<uint32_t> order(n_frames);
+    for (uint32_t i = 0; i < n_frames; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+        const RxFrameOut &x = d->h_frames[a], &y = d->h_frames[b];
+        return x.stream != y.stream ? x.stream < y.stream : x.seq < y.seq;
+    });
+    for (uint32_t i : order) {
+        const RxFrameOut &f = d->h_frames[i];
+        std::string &so = d->stdout_last[f.stream];
+        if (f.n_hdr_print) append_hex(so, f.hdr_print, f.n_hdr_print, false, false);    // :832
+        append_hex(so, f.bytes + 18, f.len - 18, true, true);                           // :872
+        if (cb) cb(user, f.stream, f.bytes, f.len);
+    }
+    return LORA_B200_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char *lora_b200_last_error(void) { return g_err.c_str(); }
+int lora_b200_abi_version(void) { return LORA_B200_ABI_VERSION; }
+
+lora_b200_decoder *lora_b200_create(const lora_b200_config *cfg) {
+    if (!cfg) { fail(LORA_B200_EINVAL, "null config"); return nullptr; }
+    if (cfg->sf < 6 || cfg->sf > 13) {            // decoder_impl.cc:57-61 (the reference prints this and exit(1)s)
+        fail(LORA_B200_EINVAL, "[LoRa Decoder] ERROR : Spreading factor should be between 6 and 12 (inclusive)!\n"
+                               "                       Other values are currently not supported.");
+        return nullptr;
+    }
+    if (cfg->n_streams == 0) { fail(LORA_B200_EINVAL, "n_streams must be >= 1"); return nullptr; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fail(LORA_B200_ECUDA, "no CUDA device: liblora_b200 has no CPU fallback");
+        return nullptr;
+    }
+    lora_b200_decoder *d = new lora_b200_decoder();
+    d->cfg = *cfg;
+    if (d->cfg.max_items_per_call == 0) d->cfg.max_items_per_call = 1u << 20;
+    if (d->cfg.max_frames_per_call == 0) d->cfg.max_frames_per_call = 8;
+    int dev = cfg->device;
+    if (dev < 0) cudaGetDevice(&dev);
+    d->device = dev;
+    auto bail = [&](const char *what, cudaError_t e) {
+        fail(LORA_B200_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+        lora_b200_destroy(d);
+        return (lora_b200_decoder *)nullptr;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    d->n_sms = prop.multiProcessorCount;
+
+    // A1: derived parameters, decoder_impl.cc:69-91 (same types, same order)
+    d->samples_per_second = (uint32_t)cfg->samp_rate;                    // :74 (uint32_t member)
+    d->dt = 1.0f / d->samples_per_second;                                // :77 float divide kept in a double
+    const uint8_t cr3 = cfg->cr & 7u;                                    // 3-bit field
+    d->bits_per_second = (double)cfg->sf * (double)(4.0 / (4.0 + cr3)) / (1u << cfg->sf) * cfg->bandwidth;   // :79
+    d->symbols_per_second = (double)cfg->bandwidth / (1u << cfg->sf);    // :80
+    d->bits_per_symbol = (double)(d->bits_per_second / d->symbols_per_second);   // :82
+    d->sps = (uint32_t)(d->samples_per_second / d->symbols_per_second);  // :83
+    d->delay_after_sync = d->sps / 4u;                                   // :84
+    d->n_bins = 1u << cfg->sf;                                           // :85
+    d->n_bins_hdr = 1u << (cfg->sf - 2);                                 // :86
+    d->decim = d->sps / d->n_bins;                                       // :87
+    if (d->sps < 2 * d->n_bins / 2 || d->decim == 0) {
+        fail(LORA_B200_EINVAL, "samp_rate %.1f too low for bandwidth %u", cfg->samp_rate, cfg->bandwidth);
+        delete d;
+        return nullptr;
+    }
+    d->k1_ok = (d->sps == 8u * d->n_bins) && cfg->sf >= 7 && cfg->sf <= 12;
+    if (cfg->demod == LORA_B200_DEMOD_FFT && !d->k1_ok) {
+        fail(LORA_B200_EUNSUPPORTED, "FFT demodulator needs samp_rate/bandwidth == 8 and SF7..SF12");
+        delete d;
+        return nullptr;
+    }
+
+    build_tables(d);
+    table_stats(d);
+    if ((e = cudaMalloc(&d->d_tables, d->toff.total)) != cudaSuccess) return bail("cudaMalloc tables", e);
+    if ((e = cudaMemcpy(d->d_tables, d->h_tables.data(), d->toff.total, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("upload tables", e);
+
+    const uint32_t ns = d->cfg.n_streams;
+    if ((e = cudaStreamCreateWithFlags(&d->rx_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&d->d_states, sizeof(RxStreamState) * ns)) != cudaSuccess) return bail("cudaMalloc states", e);
+    {
+        std::vector<RxStreamState> init(ns);
+        memset(init.data(), 0, sizeof(RxStreamState) * ns);
+        for (auto &s : init) {
+            s.state = LORA_B200_DETECT;                                  // :55
+            s.snr = 1.0f;                                                // reference leaves d_snr uninitialised (oracle D4)
+            s.phdr[1] = (uint8_t)((cr3 << 5) | ((cfg->crc ? 1u : 0u) << 4));   // :72-73
+        }
+        if ((e = cudaMemcpy(d->d_states, init.data(), sizeof(RxStreamState) * ns, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("init states", e);
+    }
+    const size_t scr_per = 2 * (size_t)d->sps + d->n_bins;
+    if ((e = cudaMalloc(&d->d_scratch, sizeof(float) * scr_per * ns)) != cudaSuccess) return bail("cudaMalloc scratch", e);
+    if ((e = cudaMalloc(&d->d_consumed, sizeof(unsigned long long) * ns)) != cudaSuccess) return bail("cudaMalloc consumed", e);
+    if ((e = cudaMemset(d->d_consumed, 0, sizeof(unsigned long long) * ns)) != cudaSuccess) return bail("memset", e);
+    d->frame_cap = ns * d->cfg.max_frames_per_call;
+    if ((e = cudaMalloc(&d->d_frames, sizeof(RxFrameRec) * d->frame_cap)) != cudaSuccess) return bail("cudaMalloc frames", e);
+    if ((e = cudaMalloc(&d->d_frames_out, sizeof(RxFrameOut) * d->frame_cap)) != cudaSuccess) return bail("cudaMalloc frames_out", e);
+    if ((e = cudaMalloc(&d->d_n_frames, sizeof(uint32_t))) != cudaSuccess) return bail("cudaMalloc n_frames", e);
+    if (d->cfg.trace_capacity) {
+        if ((e = cudaMalloc(&d->d_trace, sizeof(lora_b200_step) * (size_t)d->cfg.trace_capacity * ns)) != cudaSuccess) return bail("cudaMalloc trace", e);
+        if ((e = cudaMalloc(&d->d_trace_n, sizeof(uint32_t) * ns)) != cudaSuccess) return bail("cudaMalloc trace_n", e);
+        cudaMemset(d->d_trace_n, 0, sizeof(uint32_t) * ns);
+    }
+    d->h_consumed.assign(ns, 0);
+    d->stdout_last.assign(ns, std::string());
+    d->k2_grid = d->n_sms * 4;
+    return d;
+}
+
+void lora_b200_destroy(lora_b200_decoder *d) {
+    if (!d) return;
+    cudaSetDevice(d->device);
+    cudaDeviceSynchronize();
+    cudaFree(d->d_tables); cudaFree(d->d_packed); cudaFree(d->d_k2_scratch);
+    for (int i = 0; i < 2; i++) {
+        if (d->copy_streams[i]) cudaStreamDestroy(d->copy_streams[i]);
+        if (d->copy_events[i]) cudaEventDestroy(d->copy_events[i]);
+        cudaFree(d->d_chunk[i]); cudaFree(d->d_chunk_bins[i]); cudaFree(d->d_chunk_mags[i]);
+        if (d->h_chunk[i]) cudaFreeHost(d->h_chunk[i]);
+    }
+    if (d->rx_stream) cudaStreamDestroy(d->rx_stream);
+    cudaFree(d->d_states); cudaFree(d->d_scratch); cudaFree(d->d_consumed); cudaFree(d->d_frames);
+    cudaFree(d->d_frames_out); cudaFree(d->d_n_frames); cudaFree(d->d_trace); cudaFree(d->d_trace_n);
+    cudaFree(d->d_stage);
+    if (d->h_stage) cudaFreeHost(d->h_stage);
+    delete d;
+}
+
+uint32_t lora_b200_samples_per_symbol(const lora_b200_decoder *d) { return d ? d->sps : 0; }
+uint32_t lora_b200_bins(const lora_b200_decoder *d) { return d ? d->n_bins : 0; }
+uint32_t lora_b200_decimation(const lora_b200_decoder *d) { return d ? d->decim : 0; }
+uint64_t lora_b200_launch_count(const lora_b200_decoder *d) { return d ? d->launches : 0; }
+
+int lora_b200_banner(const lora_b200_decoder *d, char *buf, size_t cap) {    // decoder_impl.cc:93-103
+    if (!d || !buf) return fail(LORA_B200_EINVAL, "null argument");
+    int n = snprintf(buf, cap, "Bits (nominal) per symbol: \t%g\nBins per symbol: \t%u\nSamples per symbol: \t%u\nDecimation: \t\t%u\n",
+                     d->bits_per_symbol, d->n_bins, d->sps, d->decim);
+    if (d->cfg.disable_drift_correction && n >= 0 && (size_t)n < cap)
+        n += snprintf(buf + n, cap - n, "Warning: clock drift correction disabled\n");
+    if (d->cfg.implicit && n >= 0 && (size_t)n < cap)
+        n += snprintf(buf + n, cap - n, "CR: \t\t%d\nCRC: \t\t%d\n", (int)(d->cfg.cr & 7), (int)(d->cfg.crc ? 1 : 0));
+    return n;
+}
+
+int lora_b200_set_sf(lora_b200_decoder *d, uint8_t) {                         // :905-909
+    return fail(LORA_B200_EUNSUPPORTED, "[LoRa Decoder] WARNING : Setting the spreading factor during execution is currently not supported.\n"
+                                        "Nothing set, kept SF of %u.", d ? d->cfg.sf : 0);
+}
+int lora_b200_set_samp_rate(lora_b200_decoder *d, float) {                    // :911-915
+    return fail(LORA_B200_EUNSUPPORTED, "[LoRa Decoder] WARNING : Setting the sample rate during execution is currently not supported.\n"
+                                        "Nothing set, kept SR of %u.", d ? d->samples_per_second : 0);
+}
+
+size_t lora_b200_tables_build_host(const lora_b200_config *cfg, void *dst, size_t cap) {
+    if (!cfg || cfg->sf < 6 || cfg->sf > 13) { fail(LORA_B200_EINVAL, "bad config"); return 0; }
+    lora_b200_decoder tmp;
+    tmp.cfg = *cfg;
+    tmp.samples_per_second = (uint32_t)cfg->samp_rate;
+    tmp.dt = 1.0f / tmp.samples_per_second;
+    tmp.symbols_per_second = (double)cfg->bandwidth / (1u << cfg->sf);
+    tmp.sps = (uint32_t)(tmp.samples_per_second / tmp.symbols_per_second);
+    tmp.n_bins = 1u << cfg->sf;
+    if (tmp.sps < tmp.n_bins) { fail(LORA_B200_EINVAL, "samp_rate too low"); return 0; }
+    build_tables(&tmp);
+    if (dst) {
+        if (cap < tmp.toff.total) { fail(LORA_B200_EINVAL, "buffer too small"); return 0; }
+        memcpy(dst, tmp.h_tables.data(), tmp.toff.total);
+    }
+    return tmp.toff.total;
+}
+
+size_t lora_b200_tables_bytes(const lora_b200_decoder *d) { return d ? d->toff.total : 0; }
+void *lora_b200_tables_device_ptr(lora_b200_decoder *d) { return d ? d->d_tables : nullptr; }
+int lora_b200_tables_export(const lora_b200_decoder *d, void *dst, size_t cap) {
+    if (!d || !dst || cap < d->toff.total) return fail(LORA_B200_EINVAL, "tables_export: buffer too small");
+    CU(cudaSetDevice(d->device));
+    CU(cudaMemcpy(dst, d->d_tables, d->toff.total, cudaMemcpyDeviceToHost));
+    return LORA_B200_OK;
+}
+int lora_b200_tables_import(lora_b200_decoder *d, const void *src, size_t bytes) {
+    if (!d || !src || bytes != d->toff.total) return fail(LORA_B200_EINVAL, "tables_import: size mismatch");
+    CU(cudaSetDevice(d->device));
+    memcpy(d->h_tables.data(), src, bytes);
+    table_stats(d);
+    CU(cudaMemcpy(d->d_tables, src, bytes, cudaMemcpyHostToDevice));
+    return LORA_B200_OK;
+}
+
+int lora_b200_demod_fft_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, float *mags, void *stream) {
+    if (!d || (!iq && n_symbols) || (!bins && n_symbols)) return fail(LORA_B200_EINVAL, "null argument");
+    if (((uintptr_t)iq & 15u) != 0) return fail(LORA_B200_EINVAL, "iq must be 16-byte aligned");
+    CU(cudaSetDevice(d->device));
+    return dispatch_k1(d, (const float2 *)iq, n_symbols, bins, mags, (cudaStream_t)stream);
+}
+
+int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, float *mags) {
+    if (!d || (!iq && n_symbols) || (!bins && n_symbols)) return fail(LORA_B200_EINVAL, "null argument");
+    if (!d->k1_ok) return fail(LORA_B200_EUNSUPPORTED, "FFT demodulator needs samp_rate/bandwidth == 8 and SF7..SF12");
+    CU(cudaSetDevice(d->device));
+    const size_t sym_bytes = sizeof(float2) * (size_t)d->sps;
+    if (!d->chunk_symbols) {                          // lazily create the double-buffered pipeline (64 MiB chunks)
+        d->chunk_symbols = std::max<size_t>(1, ((size_t)64 << 20) / sym_bytes);
+        for (int i = 0; i < 2; i++) {
+            CU(cudaStreamCreateWithFlags(&d->copy_streams[i], cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&d->copy_events[i], cudaEventDisableTiming));
+            CU(cudaMalloc(&d->d_chunk[i], d->chunk_symbols * sym_bytes));
+            CU(cudaMalloc(&d->d_chunk_bins[i], d->chunk_symbols * sizeof(uint32_t)));
+            CU(cudaMalloc(&d->d_chunk_mags[i], d->chunk_symbols * sizeof(float)));
+        }
+    }
+    cudaPointerAttributes attr;
+    bool pinned = cudaPointerGetAttributes(&attr, iq) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (!pinned && !d->h_chunk[0])
+        for (int i = 0; i < 2; i++) CU(cudaMallocHost(&d->h_chunk[i], d->chunk_symbols * sym_bytes));
+    const uint8_t *src = (const uint8_t *)iq;
+    size_t done = 0;
+    int k = 0;
+    while (done < n_symbols) {
+        const size_t n = std::min(d->chunk_symbols, n_symbols - done);
+        const int b = k & 1;
+        cudaStream_t st = d->copy_streams[b];
+        CU(cudaStreamSynchronize(st));                // buffer b is free again (its D2H finished)
+        const void *h = src + done * sym_bytes;
+        if (!pinned) { memcpy(d->h_chunk[b], h, n * sym_bytes); h = d->h_chunk[b]; }
+        CU(cudaMemcpyAsync(d->d_chunk[b], h, n * sym_bytes, cudaMemcpyHostToDevice, st));
+        int rc = dispatch_k1(d, (const float2 *)d->d_chunk[b], n, d->d_chunk_bins[b], d->d_chunk_mags[b], st);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(bins + done, d->d_chunk_bins[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        if (mags) CU(cudaMemcpyAsync(mags + done, d->d_chunk_mags[b], n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        done += n;
+        k++;
+    }
+    CU(cudaStreamSynchronize(d->copy_streams[0]));
+    CU(cudaStreamSynchronize(d->copy_streams[1]));
+    return LORA_B200_OK;
+}
+
+int lora_b200_demod_gradient_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, void *stream) {
+    if (!d || (!iq && n_symbols) || (!bins && n_symbols)) return fail(LORA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(d->device));
+    if (!d->d_k2_scratch) CU(cudaMalloc(&d->d_k2_scratch, sizeof(float) * (size_t)d->k2_grid * (d->sps + d->n_bins)));
+    if (n_symbols == 0) return LORA_B200_OK;
+    const int grid = (int)std::min<size_t>(n_symbols, (size_t)d->k2_grid);
+    k2_gradient_kernel<<<grid, RX_THREADS, 0, (cudaStream_t)stream>>>((const float2 *)iq, n_symbols, d->sps, d->n_bins, d->decim,
+                                                                     d->d_k2_scratch, bins);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+int lora_b200_decode_codewords_dev(lora_b200_decoder *d, const uint8_t *codewords, const uint32_t *lengths, size_t stride,
+                                   const uint8_t *cr, const uint8_t *is_header, size_t n_vec, uint8_t *out,
+                                   size_t out_stride, uint32_t *out_len, void *stream) {
+    if (!d || !codewords || !lengths || !cr || !is_header || !out || !out_len) return fail(LORA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(d->device));
+    if (n_vec == 0) return LORA_B200_OK;
+    const int grid = (int)std::min<size_t>(n_vec, (size_t)d->n_sms * 8);
+    k8_decode_vectors_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(codewords, lengths, stride, cr, is_header, n_vec, out, out_stride, out_len);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+int lora_b200_deinterleave_dev(lora_b200_decoder *d, const uint32_t *words, uint32_t n_words, uint32_t ppm, size_t n_blocks,
+                               uint8_t *codewords, void *stream) {
+    if (!d || !words || !codewords) return fail(LORA_B200_EINVAL, "null argument");
+    if (n_words == 0 || n_words > 8 || ppm == 0 || ppm > 16) return fail(LORA_B200_EINVAL, "n_words must be 1..8, ppm 1..16");
+    CU(cudaSetDevice(d->device));
+    if (n_blocks == 0) return LORA_B200_OK;
+    k8_deinterleave_kernel<<<(unsigned)((n_blocks + 127) / 128), 128, 0, (cudaStream_t)stream>>>(words, n_words, ppm, n_blocks, codewords);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+static int ensure_stage(lora_b200_decoder *d) {
+    if (d->d_stage) return LORA_B200_OK;
+    const size_t bytes = sizeof(float2) * (size_t)d->cfg.max_items_per_call * d->cfg.n_streams;
+    CU(cudaMalloc(&d->d_stage, bytes));
+    CU(cudaMallocHost(&d->h_stage, bytes));
+    return LORA_B200_OK;
+}
+
+int lora_b200_work(lora_b200_decoder *d, uint32_t stream, const void *iq_host, size_t n_items, size_t *consumed,
+                   lora_b200_frame_cb cb, void *user) {
+    if (!d || !consumed || (!iq_host && n_items)) return fail(LORA_B200_EINVAL, "null argument");
+    if (stream >= d->cfg.n_streams) return fail(LORA_B200_EINVAL, "stream %u out of range", stream);
+    CU(cudaSetDevice(d->device));
+    if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;     // never read past what was staged
+    *consumed = 0;
+    if (n_items < 2 * (size_t)d->sps) return LORA_B200_OK;                             // output_multiple, :91
+    int rc = ensure_stage(d);
+    if (rc) return rc;
+    float2 *h = d->h_stage + (size_t)stream * d->cfg.max_items_per_call;
+    float2 *dv = d->d_stage + (size_t)stream * d->cfg.max_items_per_call;
+    memcpy(h, iq_host, sizeof(float2) * n_items);
+    CU(cudaMemcpyAsync(dv, h, sizeof(float2) * n_items, cudaMemcpyHostToDevice, d->rx_stream));
+    return run_rx(d, dv, d->cfg.max_items_per_call, n_items, stream, 1, consumed, cb, user);
+}
+
+int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, size_t stride_items, int host_ptr,
+                         size_t *consumed, lora_b200_frame_cb cb, void *user) {
+    if (!d || !consumed || (!iq && n_items)) return fail(LORA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(d->device));
+    const uint32_t ns = d->cfg.n_streams;
+    for (uint32_t s = 0; s < ns; s++) consumed[s] = 0;
+    if (n_items < 2 * (size_t)d->sps) return LORA_B200_OK;
+    const float2 *dv = (const float2 *)iq;
+    size_t stride = stride_items;
+    if (host_ptr) {
+        if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;
+        int rc = ensure_stage(d);
+        if (rc) return rc;
+        CU(cudaMemcpy2DAsync(d->d_stage, sizeof(float2) * d->cfg.max_items_per_call, iq, sizeof(float2) * stride_items,
+                             sizeof(float2) * n_items, ns, cudaMemcpyHostToDevice, d->rx_stream));
+        dv = d->d_stage;
+        stride = d->cfg.max_items_per_call;
+    }
+    return run_rx(d, dv, stride, n_items, 0, ns, consumed, cb, user);
+}
+
+int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream) {
+    if (!d || stream >= d->cfg.n_streams) return fail(LORA_B200_EINVAL, "bad stream");
+    CU(cudaSetDevice(d->device));
+    int32_t st = 0;
+    CU(cudaMemcpy(&st, &d->d_states[stream].state, sizeof st, cudaMemcpyDeviceToHost));
+    return st;
+}
+
+int lora_b200_stdout_last(lora_b200_decoder *d, uint32_t stream, char *buf, size_t cap) {
+    if (!d || !buf || stream >= d->cfg.n_streams) return fail(LORA_B200_EINVAL, "bad argument");
+    return snprintf(buf, cap, "%s", d->stdout_last[stream].c_str());
+}
+
+int lora_b200_trace_read(lora_b200_decoder *d, uint32_t stream, lora_b200_step *steps, size_t cap, size_t *n) {
+    if (!d || !steps || !n || stream >= d->cfg.n_streams) return fail(LORA_B200_EINVAL, "bad argument");
+    if (!d->d_trace) return fail(LORA_B200_EINVAL, "trace_capacity was 0 at creation");
+    CU(cudaSetDevice(d->device));
+    uint32_t cnt = 0;
+    CU(cudaMemcpy(&cnt, d->d_trace_n + stream, sizeof cnt, cudaMemcpyDeviceToHost));
+    size_t m = std::min<size_t>(std::min<size_t>(cnt, d->cfg.trace_capacity), cap);
+    if (m) CU(cudaMemcpy(steps, d->d_trace + (size_t)stream * d->cfg.trace_capacity, sizeof(lora_b200_step) * m, cudaMemcpyDeviceToHost));
+    *n = cnt;
+    return cnt > d->cfg.trace_capacity ? LORA_B200_EOVERFLOW : LORA_B200_OK;
+}
+
+}  // extern "C"

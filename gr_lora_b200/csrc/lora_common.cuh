@@ -1,0 +1,110 @@
+// lora_common.cuh -- small host/device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define LB_HD __host__ __device__ __forceinline__
+#define LB_D __device__ __forceinline__
+#else
+#define LB_HD inline
+#define LB_D inline
+#endif
+
+namespace lb {
+
+LB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+LB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// plain complex product (the reference multiplies by the down-chirp, not its conjugate,
+// lib/decoder_impl.cc:436-438)
+LB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * w + c
+LB_HD float2 cfma(float2 a, float2 w, float2 c) {
+    return make_float2(fmaf(a.x, w.x, fmaf(-a.y, w.y, c.x)), fmaf(a.x, w.y, fmaf(a.y, w.x, c.y)));
+}
+LB_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+LB_HD float cnorm2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+
+// cos/sin(2*pi*e/32), e = 0..15, as literals so that they fold after unrolling
+LB_HD float cos32(int e) {
+    switch (e & 15) {
+    case 0: return 1.0f;
+    case 1: return 0.98078528040323043f;
+    case 2: return 0.92387953251128674f;
+    case 3: return 0.83146961230254524f;
+    case 4: return 0.70710678118654757f;
+    case 5: return 0.55557023301960229f;
+    case 6: return 0.38268343236508984f;
+    case 7: return 0.19509032201612833f;
+    case 8: return 0.0f;
+    case 9: return -0.19509032201612833f;
+    case 10: return -0.38268343236508984f;
+    case 11: return -0.55557023301960229f;
+    case 12: return -0.70710678118654757f;
+    case 13: return -0.83146961230254524f;
+    case 14: return -0.92387953251128674f;
+    default: return -0.98078528040323043f;
+    }
+}
+// sin(2*pi*e/32) = cos(2*pi*|e-8|/32) for e in [0,16)
+LB_HD float sin32(int e) { return cos32(e > 8 ? e - 8 : 8 - e); }
+
+// multiply by W_32^e = exp(-2*pi*i*e/32), e in [0,16), e known at compile time after unrolling
+LB_HD float2 mul_w32(float2 a, int e) {
+    const float h = 0.70710678118654757f;
+    switch (e) {
+    case 0: return a;
+    case 8: return make_float2(a.y, -a.x);                       // * (-i)
+    case 4: return make_float2((a.x + a.y) * h, (a.y - a.x) * h);    // * (1 - i)/sqrt2
+    case 12: return make_float2((a.y - a.x) * h, -(a.x + a.y) * h);  // * (-1 - i)/sqrt2
+    default: {
+        const float c = cos32(e);
+        const float s = sin32(e);
+        // W = c - i s  ->  (a.x + i a.y)(c - i s) = (a.x c + a.y s) + i (a.y c - a.x s)
+        return make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
+    }
+    }
+}
+
+// in-register radix-2 DIF DFT of R points (forward, e^{-j}); X[k] ends up at v[bitrev(k)]
+template <int R>
+LB_HD void dft_dif(float2 *v) {
+#pragma unroll
+    for (int len = R; len >= 2; len >>= 1) {
+        const int half = len >> 1;
+#pragma unroll
+        for (int g0 = 0; g0 < R; g0 += len) {
+#pragma unroll
+            for (int k = 0; k < half; k++) {
+                const float2 a = v[g0 + k], b = v[g0 + k + half];
+                v[g0 + k] = cadd(a, b);
+                v[g0 + k + half] = mul_w32(csub(a, b), k * (32 / len));
+            }
+        }
+    }
+}
+
+template <int R>
+LB_HD constexpr int bitrev(int k) {
+    int r = 0;
+    for (int b = 1, t = R >> 1; b < R; b <<= 1, t >>= 1)
+        if (k & b) r |= t;
+    return r;
+}
+
+// argmax key: larger |.|^2 wins, ties go to the smaller index (std::max_element keeps the
+// first maximum, lib/decoder_impl.cc:463).  mag2 >= 0 so its bit pattern is monotonic.
+LB_HD unsigned long long pack_key(float mag2, uint32_t idx) {
+    union { float f; uint32_t u; } c;
+    c.f = mag2;
+    return ((unsigned long long)c.u << 32) | (unsigned long long)(0xFFFFFFFFu - idx);
+}
+LB_HD uint32_t key_idx(unsigned long long k) { return 0xFFFFFFFFu - (uint32_t)(k & 0xFFFFFFFFull); }
+LB_HD float key_mag2(unsigned long long k) {
+    union { float f; uint32_t u; } c;
+    c.u = (uint32_t)(k >> 32);
+    return c.f;
+}
+
+}  // namespace lb

@@ -1,0 +1,163 @@
+/*
+ * lora_b200.h -- C ABI of liblora_b200.so, the B200 (sm_100a) replacement for the hot path of
+ * rpp0/gr-lora: gr::lora::decoder_impl::work() and the DSP helpers it calls
+ * (lib/decoder_impl.cc:141-903 of the reference).
+ *
+ * Drop-in boundary: the GNU Radio scheduler, PMT message ports and the
+ * hier-block wiring stay on the host.  A thin gr::lora::decoder_impl shim (see
+ * INTEGRATION.md) forwards its constructor arguments to lora_b200_create() and its
+ * work() buffer to lora_b200_work(); everything numerical happens behind this header.
+ * Plain C types only: no torch, no C++ in the signatures.
+ *
+ * All functions return 0 on success or a negative LORA_B200_E* code; the message of the
+ * last failure on the calling thread is available from lora_b200_last_error().
+ * There is NO CPU fallback: without a CUDA device lora_b200_create() fails.
+ */
+#ifndef LORA_B200_H
+#define LORA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LORA_B200_ABI_VERSION 1
+
+enum {
+    LORA_B200_OK = 0,
+    LORA_B200_EINVAL = -1,     /* bad argument (the reference exit(1)s for sf outside [6,13], decoder_impl.cc:57-61) */
+    LORA_B200_ECUDA = -2,      /* CUDA runtime failure / no device */
+    LORA_B200_ENOMEM = -3,
+    LORA_B200_EUNSUPPORTED = -4,
+    LORA_B200_EOVERFLOW = -5   /* per-call frame or trace capacity exhausted */
+};
+
+/* demodulator selection for demodulate() (decoder_impl.cc:499-500) */
+enum {
+    LORA_B200_DEMOD_GRADIENT = 0,  /* max_frequency_gradient_idx: what the reference runs today (:499)      */
+    LORA_B200_DEMOD_FFT = 1        /* dechirp + FFT + argmax (get_shift_fft :430-464), mapped (bin-1) mod N */
+};
+
+/* decoder states, lib/decoder_impl.h:40-48 */
+enum { LORA_B200_DETECT = 0, LORA_B200_SYNC, LORA_B200_FIND_SFD, LORA_B200_PAUSE,
+       LORA_B200_DECODE_HEADER, LORA_B200_DECODE_PAYLOAD, LORA_B200_STOP };
+
+/* Replaces the argument list of lora::decoder::make (include/lora/decoder.h:705,
+ * lib/decoder_impl.cc:41-44,49): the first eight fields are exactly those arguments. */
+typedef struct lora_b200_config {
+    float    samp_rate;
+    uint32_t bandwidth;
+    uint8_t  sf;
+    uint8_t  implicit;
+    uint8_t  cr;
+    uint8_t  crc;
+    uint8_t  reduced_rate;
+    uint8_t  disable_drift_correction;
+    uint8_t  demod;              /* LORA_B200_DEMOD_*                                         */
+    uint8_t  reserved0;
+    uint32_t n_streams;          /* independent (channel, SF) streams sharing this config; >=1 */
+    int32_t  device;             /* CUDA device ordinal; -1 = current device                   */
+    uint32_t max_items_per_call; /* capacity of the per-stream staging buffer (0 = 1<<20)      */
+    uint32_t max_frames_per_call;/* per stream (0 = 64)                                        */
+    uint32_t trace_capacity;     /* per-stream lora_b200_step records kept per call (0 = none) */
+} lora_b200_config;
+
+typedef struct lora_b200_decoder lora_b200_decoder;
+
+/* one state-machine step, for parity tests against the oracle's work() trace */
+typedef struct lora_b200_step {
+    int32_t state;       /* state at entry of the step                        */
+    int32_t consumed;    /* what the reference would pass to consume_each      */
+    int32_t bin;         /* raw demodulated bin, -1 when the step has none     */
+    int32_t fine_sync;   /* d_fine_sync after the step                         */
+    float   metric;      /* autocorr (DETECT), max corr (SYNC), pearson (FIND_SFD) */
+} lora_b200_step;
+
+/* Frame callback: replaces message_port_pub("frames", blob) (decoder_impl.cc:607-608).
+ * `frame` = 15-byte loratap header | 3-byte loraphy header | payload (decoder_impl.cc:588-601);
+ * valid only during the callback. */
+typedef void (*lora_b200_frame_cb)(void *user, uint32_t stream, const uint8_t *frame, size_t len);
+
+/* ---- lifecycle: decoder::make / ~decoder_impl (decoder_impl.cc:41-139) ---- */
+lora_b200_decoder *lora_b200_create(const lora_b200_config *cfg);
+void lora_b200_destroy(lora_b200_decoder *d);
+const char *lora_b200_last_error(void);
+int lora_b200_abi_version(void);
+
+/* derived parameters (decoder_impl.cc:69-91) and the constructor's stdout banner (:93-103) */
+uint32_t lora_b200_samples_per_symbol(const lora_b200_decoder *d);
+uint32_t lora_b200_bins(const lora_b200_decoder *d);
+uint32_t lora_b200_decimation(const lora_b200_decoder *d);
+int lora_b200_banner(const lora_b200_decoder *d, char *buf, size_t cap);
+/* set_sf / set_samp_rate are unsupported at run time in the reference too (:905-915): they
+ * return LORA_B200_EUNSUPPORTED and leave the decoder untouched. */
+int lora_b200_set_sf(lora_b200_decoder *d, uint8_t sf);
+int lora_b200_set_samp_rate(lora_b200_decoder *d, float samp_rate);
+
+/* ---- chirp / twiddle tables (build_ideal_chirps, decoder_impl.cc:141-175) ----
+ * One contiguous device blob: downchirp cf32[sps] | upchirp cf32[sps] | down_ifreq f32[sps] |
+ * up_ifreq f32[sps] | up_ifreq_v f32[3*sps] | FFT twiddles cf32[sps].  Rank 0 builds it, the
+ * other ranks receive it by ONE ncclBroadcast at init and call _commit. */
+size_t lora_b200_tables_bytes(const lora_b200_decoder *d);
+/* host-only: build the blob for `cfg` into dst (no device needed); returns its size in bytes
+ * (dst == NULL: size query), 0 on error.  Layout: the six arrays above, back to back,
+ * total rounded up to 256 bytes. */
+size_t lora_b200_tables_build_host(const lora_b200_config *cfg, void *dst, size_t cap);
+void *lora_b200_tables_device_ptr(lora_b200_decoder *d);
+int lora_b200_tables_export(const lora_b200_decoder *d, void *host_dst, size_t cap);
+int lora_b200_tables_import(lora_b200_decoder *d, const void *host_src, size_t bytes);
+
+/* ---- K1: dechirp + FFT + argmax on aligned symbol windows (get_shift_fft, :430-464) ----
+ * iq: n_symbols * sps interleaved cf32.  bins[i] in [0, N), mags[i] = |tmp[bin]| (may be NULL).
+ * _dev: all pointers are device pointers, the launch is asynchronous on `cuda_stream`
+ * (a cudaStream_t passed as void*, NULL = default stream).
+ * _host: host pointers; copies (pinned, chunked, overlapped with compute) are inside. */
+int lora_b200_demod_fft_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols,
+                            uint32_t *bins, float *mags, void *cuda_stream);
+int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symbols,
+                             uint32_t *bins, float *mags);
+/* K2: max_frequency_gradient_idx on aligned windows (:466-491), same layout */
+int lora_b200_demod_gradient_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols,
+                                 uint32_t *bins, void *cuda_stream);
+
+/* ---- K8: integer decode of whole code-word vectors (decode(), :567-586, B2-B4) ----
+ * For each of n_vec vectors: codewords[i*stride .. +lengths[i]) -> deshuffle, dewhiten,
+ * Hamming decode.  out[i*out_stride ..]; out_len[i] = bytes produced.  cr[i] = d_phdr.cr,
+ * is_header[i] as in decode(is_header).  Device pointers, async on cuda_stream. */
+int lora_b200_decode_codewords_dev(lora_b200_decoder *d, const uint8_t *codewords, const uint32_t *lengths,
+                                   size_t stride, const uint8_t *cr, const uint8_t *is_header, size_t n_vec,
+                                   uint8_t *out, size_t out_stride, uint32_t *out_len, void *cuda_stream);
+/* B1 + Gray: words (u32, one per symbol) of one interleaver block -> ppm code words; batch of blocks */
+int lora_b200_deinterleave_dev(lora_b200_decoder *d, const uint32_t *words, uint32_t n_words, uint32_t ppm,
+                               size_t n_blocks, uint8_t *codewords, void *cuda_stream);
+
+/* ---- the drop-in: decoder_impl::work (decoder_impl.cc:740-903) ----
+ * Feeds `n_items` cf32 items of stream `stream` (HOST pointer, as GNU Radio hands them to
+ * work(); not retained after return).  Runs the whole state machine on the GPU for as many
+ * steps as fit (each step needs 2*sps items of look-ahead, the block's output_multiple :91),
+ * sets *consumed to the number of items the caller must drop (the sum of the reference's
+ * consume_each() calls) and invokes cb once per completed frame, in order.
+ * The caller re-presents the unconsumed tail at the start of the next call. */
+int lora_b200_work(lora_b200_decoder *d, uint32_t stream, const void *iq_host, size_t n_items,
+                   size_t *consumed, lora_b200_frame_cb cb, void *user);
+/* Same for all streams at once: iq is [n_streams][n_items] (row stride `stride_items`).
+ * host_ptr != 0: iq is host memory (copied inside); 0: iq is device memory. */
+int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, size_t stride_items,
+                         int host_ptr, size_t *consumed /* [n_streams] */, lora_b200_frame_cb cb, void *user);
+/* current state of a stream (LORA_B200_DETECT ...) */
+int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream);
+/* the reference's std::cout hex lines for the frames delivered by the last work call of this
+ * stream (" 04 90 40" + " de ad ... (ascii)\n", decoder_impl.cc:832,872) */
+int lora_b200_stdout_last(lora_b200_decoder *d, uint32_t stream, char *buf, size_t cap);
+/* per-step trace of the last work call (needs trace_capacity > 0) */
+int lora_b200_trace_read(lora_b200_decoder *d, uint32_t stream, lora_b200_step *steps, size_t cap, size_t *n);
+
+/* how many kernels this library has launched since creation (bench.py's gpu_launches) */
+uint64_t lora_b200_launch_count(const lora_b200_decoder *d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LORA_B200_H */
