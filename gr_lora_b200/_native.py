@@ -46,6 +46,7 @@ SIGNATURES = {
     "lora_b200_tables_device_ptr": (_vp, [_vp]),
     "lora_b200_tables_export": (_i, [_vp, _vp, _sz]),
     "lora_b200_tables_import": (_i, [_vp, _vp, _sz]),
+    "lora_b200_tables_commit": (_i, [_vp]),
     "lora_b200_demod_fft_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "lora_b200_demod_fft_host": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "lora_b200_demod_gradient_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),

@@ -485,6 +485,14 @@ int lora_b200_tables_import(lora_b200_decoder *d, const void *src, size_t bytes)
     return LORA_B200_OK;
 }
 
+int lora_b200_tables_commit(lora_b200_decoder *d) {
+    if (!d) return fail(LORA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(d->device));
+    CU(cudaMemcpy(d->h_tables.data(), d->d_tables, d->toff.total, cudaMemcpyDeviceToHost));
+    table_stats(d);
+    return LORA_B200_OK;
+}
+
 int lora_b200_demod_fft_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, float *mags, void *stream) {
     if (!d || (!iq && n_symbols) || (!bins && n_symbols)) return fail(LORA_B200_EINVAL, "null argument");
     if (((uintptr_t)iq & 15u) != 0) return fail(LORA_B200_EINVAL, "iq must be 16-byte aligned");

@@ -222,6 +222,18 @@ class decoder:
         b = np.ascontiguousarray(blob, dtype=np.uint8)
         N.check(self._L.lora_b200_tables_import(self._h, b.ctypes.data, b.size), "lora_b200_tables_import")
 
+    def tables_device_view(self):
+        """Zero-copy view of the device table blob as an object with __cuda_array_interface__
+        (wrap with torch.as_tensor(view, device="cuda") for the init-time NCCL broadcast)."""
+        ptr, n = int(self._L.lora_b200_tables_device_ptr(self._h)), self.tables_bytes()
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        return _View()
+
+    def tables_commit(self):
+        N.check(self._L.lora_b200_tables_commit(self._h), "lora_b200_tables_commit")
+
     def launch_count(self):
         return int(self._L.lora_b200_launch_count(self._h))
 

@@ -108,6 +108,9 @@ size_t lora_b200_tables_build_host(const lora_b200_config *cfg, void *dst, size_
 void *lora_b200_tables_device_ptr(lora_b200_decoder *d);
 int lora_b200_tables_export(const lora_b200_decoder *d, void *host_dst, size_t cap);
 int lora_b200_tables_import(lora_b200_decoder *d, const void *host_src, size_t bytes);
+/* after writing the device blob in place (e.g. ncclBroadcast into lora_b200_tables_device_ptr):
+ * refresh the host copy and the constants derived from it */
+int lora_b200_tables_commit(lora_b200_decoder *d);
 
 /* ---- K1: dechirp + FFT + argmax on aligned symbol windows (get_shift_fft, :430-464) ----
  * iq: n_symbols * sps interleaved cf32.  bins[i] in [0, N), mags[i] = |tmp[bin]| (may be NULL).

@@ -1,0 +1,150 @@
+"""GPU parity: K1 (dechirp + FFT + argmax) and K2 (gradient demod) through the C ABI vs the oracle."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    return torch
+
+
+def gpu_fft(torch, dec, x):
+    n = x.size // dec.sps
+    iq = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    bins = torch.full((max(n, 1),), -1, dtype=torch.int32, device="cuda")
+    mags = torch.zeros(max(n, 1), dtype=torch.float32, device="cuda")
+    dec.demod_fft(iq, n, bins, mags, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return bins.cpu().numpy()[:n].astype(np.uint32), mags.cpu().numpy()[:n]
+
+
+@pytest.mark.parametrize("sf", range(7, 13))
+def test_k1_golden_fixture(torch, oracle, sf):
+    import gr_lora_b200 as G
+    from golden.make_golden import k1_case
+    g = GOLD["k1"][str(sf)]
+    vals, x = k1_case(sf, g["n"], g["snr_db"], g["seed"])
+    dec = G.decoder(1e6, 125000, sf, False, 4, True, demod="fft", quiet=True)
+    bins, mags = gpu_fft(torch, dec, x)
+    assert [int(b) for b in bins] == g["fft_bins"]                      # bit-exact bins vs committed oracle output
+    np.testing.assert_allclose(mags, np.array(g["fft_mags"], np.float32), rtol=1e-4)
+    ob, om = oracle.Decoder(sf=sf).demod_fft_batch(x)
+    assert np.array_equal(bins, ob)
+    dec.close()
+
+
+@pytest.mark.parametrize("sf,n,snr", [(7, 1000, -6.0), (8, 500, -8.0), (9, 300, -10.0), (10, 100, -12.0), (11, 40, -14.0), (12, 20, -16.0)])
+def test_k1_low_snr_within_one_bin_of_oracle(torch, oracle, sf, n, snr):
+    """north_star tolerance: bin index within +-1 of the reference (fp32).  At low SNR the two fp32
+    evaluation orders may break a near-tie differently; anything beyond +-1 must be a genuine
+    tie between distant bins (magnitudes equal to 1e-4)."""
+    import gr_lora_b200 as G
+    from gr_lora_b200 import tx
+    rng = np.random.default_rng(100 + sf)
+    vals = rng.integers(0, 1 << sf, n)
+    x = tx.synth_symbols(vals, sf, snr_db=snr, seed=200 + sf)
+    dec = G.decoder(1e6, 125000, sf, False, 4, True, demod="fft", quiet=True)
+    bins, mags = gpu_fft(torch, dec, x)
+    ob, om = oracle.Decoder(sf=sf).demod_fft_batch(x)
+    nb = 1 << sf
+    diff = np.minimum((bins.astype(np.int64) - ob) % nb, (ob - bins.astype(np.int64)) % nb)
+    far = diff > 1
+    assert np.mean(diff == 0) >= 0.99
+    np.testing.assert_allclose(mags, om, rtol=2e-4)
+    assert not np.any(far & (np.abs(mags - om) > 1e-4 * om))
+    dec.close()
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 300])
+def test_k1_ragged_and_empty(torch, oracle, n):
+    import gr_lora_b200 as G
+    from gr_lora_b200 import tx
+    sf = 7
+    vals = np.arange(n) % 128
+    x = tx.synth_symbols(vals, sf, snr_db=5.0, seed=n) if n else np.zeros(0, np.complex64)
+    dec = G.decoder(1e6, 125000, sf, False, 4, True, demod="fft", quiet=True)
+    bins, mags = gpu_fft(torch, dec, x) if n else (np.zeros(0, np.uint32), None)
+    if n:
+        assert np.array_equal(bins, oracle.Decoder(sf=sf).demod_fft_batch(x)[0])
+        assert np.array_equal(bins, vals.astype(np.uint32))
+    else:
+        dec.demod_fft(0, 0, 0, 0)        # n_symbols == 0 is a no-op
+    dec.close()
+
+
+def test_k1_silence_and_alignment_errors(torch):
+    import gr_lora_b200 as G
+    dec = G.decoder(1e6, 125000, 7, False, 4, True, demod="fft", quiet=True)
+    bins, mags = gpu_fft(torch, dec, np.zeros(4 * 1024, np.complex64))
+    assert np.all(bins == 0) and np.all(mags == 0)          # all-equal magnitudes: first maximum (std::max_element)
+    iq = torch.zeros(2 * 1024 + 1, dtype=torch.complex64, device="cuda")
+    b = torch.zeros(2, dtype=torch.int32, device="cuda")
+    with pytest.raises(Exception, match="16-byte"):
+        dec.demod_fft(iq.data_ptr() + 8, 2, b)
+    dec.close()
+
+
+def test_k1_full_size_property_config2(torch):
+    """BASELINE.json configs[1] at reduced channel count x full symbol count is covered by bench.py;
+    here a 256-channel x 256-symbol batch (2 GiB) must demodulate >= 99.9 % of +10 dB symbols to the
+    transmitted value, and must be invariant to the order of the symbols (a checksum of checksums)."""
+    import gr_lora_b200 as G
+    sys_path_bench = __import__("bench")
+    dev = torch.device("cuda", 0)
+    iq, vals = sys_path_bench.synth_batch(torch, 7, 256, 256, 10.0, dev, 0x4C6F5202)
+    n = iq.shape[0]
+    dec = G.decoder(1e6, 125000, 7, False, 4, True, demod="fft", quiet=True)
+    bins = torch.empty(n, dtype=torch.int32, device=dev)
+    dec.demod_fft(iq, n, bins, None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert float((bins.to(torch.int64) == vals).float().mean()) >= 0.999
+    perm = torch.randperm(n, device=dev)
+    iq2 = iq[perm].contiguous()
+    bins2 = torch.empty_like(bins)
+    dec.demod_fft(iq2, n, bins2, None, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(bins2, bins[perm])
+    dec.close()
+
+
+def test_k1_host_api_matches_device_api(torch, oracle):
+    import gr_lora_b200 as G
+    from gr_lora_b200 import tx
+    sf, n = 8, 700
+    vals = np.random.default_rng(1).integers(0, 256, n)
+    x = tx.synth_symbols(vals, sf, snr_db=0.0, seed=2)
+    dec = G.decoder(1e6, 125000, sf, False, 4, True, demod="fft", quiet=True)
+    hb, hm = dec.demod_fft_host(x)                       # pageable host memory: staged through pinned chunks
+    db, dm = gpu_fft(torch, dec, x)
+    assert np.array_equal(hb, db) and np.array_equal(hm, dm)
+    assert np.array_equal(hb, oracle.Decoder(sf=sf).demod_fft_batch(x)[0])
+    dec.close()
+
+
+@pytest.mark.parametrize("sf", [7, 9, 12])
+def test_k2_gradient_batch_vs_oracle(torch, oracle, sf):
+    """max_frequency_gradient_idx (lib/decoder_impl.cc:466-491) on clean and on 30 dB symbols."""
+    import gr_lora_b200 as G
+    from gr_lora_b200 import tx
+    nb = 1 << sf
+    vals = np.concatenate([[0, 1, nb - 1, nb // 2], np.random.default_rng(sf).integers(0, nb, 60)])
+    for snr in (None, 30.0):
+        x = tx.synth_symbols(vals, sf, snr_db=snr, seed=5)
+        dec = G.decoder(1e6, 125000, sf, False, 4, True, quiet=True)
+        iq = torch.from_numpy(x).cuda()
+        bins = torch.empty(len(vals), dtype=torch.int32, device="cuda")
+        dec.demod_gradient(iq, len(vals), bins)
+        torch.cuda.synchronize()
+        ob = oracle.Decoder(sf=sf).demod_grad_batch(x)
+        assert np.array_equal(bins.cpu().numpy().astype(np.uint32), ob)
+        dec.close()
