@@ -264,6 +264,7 @@ def main():
         step()
     torch.cuda.synchronize()
     acc = float((bins.to(torch.int64) == vals).float().mean().item())
+    bins_ref = bins.clone()
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -356,11 +357,10 @@ def main():
             dt_t = torch.tensor([tb - ta], dtype=torch.float64, device=device)
             if world > 1:
                 dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
-            e2e_ok = bool((h_bins.to(torch.int64) == vals.cpu()).float().mean().item() == acc or True)
             e2e = {"value": world * n_sym_total * e_steps / float(dt_t.item()), "unit": "symbols/s",
                    "h2d_bytes_per_step": int(n_sym_total * sps * 8), "d2h_bytes_per_step": int(n_sym_total * 8),
                    "steps": e_steps, "timer": "host wall clock around lora_b200_demod_fft_host (pinned host buffers)",
-                   "bins_match_device_path": bool(torch.equal(h_bins.to(device), bins)) and e2e_ok}
+                   "bins_match_device_path": bool(torch.equal(h_bins.to(device), bins_ref))}
             del h_iq
         except Exception as exc:     # e.g. not enough pinnable host memory on the box
             e2e = {"value": None, "unit": "symbols/s", "error": str(exc)[:200]}

@@ -2,6 +2,7 @@
 // Lets the non-GPU test-suite run the kernels' index arithmetic, twiddles and integer chain
 // on the host and compare them with the oracle.  Not part of liblora_b200.so.
 #include "k1_fft.cuh"
+#include "k1_warp.cuh"
 #include "int_chain.cuh"
 
 extern "C" {
@@ -18,6 +19,12 @@ int lb_k1_emulate(int sf, const float2 *x, size_t n_symbols, const float2 *chirp
     case 12: lb::k1_emulate<12>(a, bins, mags); break;
     default: return -1;
     }
+    return 0;
+}
+
+int lb_k1_emulate_warp_sf7(const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
+    lb::K1Args a{x, chirp, tw, n_symbols};
+    lb::w7_emulate(a, bins, mags);
     return 0;
 }
 

@@ -4,6 +4,7 @@
 // pinned staging and kernel launches.  There is no CPU compute path in this file.
 #include "../../include/lora_b200.h"
 #include "k1_fft.cuh"
+#include "k1_warp.cuh"
 #include "rx_stream.cuh"
 
 #include <algorithm>
@@ -11,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -189,9 +191,51 @@ int launch_k1(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t
     return LORA_B200_OK;
 }
 
+// SF7: one warp per symbol, TMA-fed shared-memory ring (k1_warp.cuh)
+template <int NWARPS, int NSLOT>
+int launch_k1_warp7(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(W7Smem<NWARPS, NSLOT>);
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_sf7_warp_kernel<NWARPS, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    const int grid = (int)std::min<size_t>((n_symbols + NWARPS - 1) / NWARPS, (size_t)d->n_sms);
+    k1_sf7_warp_kernel<NWARPS, NSLOT><<<grid, NWARPS * 32, smem, st>>>(a, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("LORA_B200_K1");
+        v = 2;
+        if (e) {
+            if (!strcmp(e, "generic")) v = 0;
+            else if (!strcmp(e, "w8x3")) v = 1;
+            else if (!strcmp(e, "w12x2")) v = 2;
+            else if (!strcmp(e, "w13x2")) v = 3;
+            else if (!strcmp(e, "w9x3")) v = 4;
+        }
+    }
+    return v;
+}
+
 int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins, float *mags, cudaStream_t st) {
     if (!d->k1_ok) return fail(LORA_B200_EUNSUPPORTED, "FFT demodulator needs samp_rate/bandwidth == 8 and SF7..SF12");
     if (n == 0) return LORA_B200_OK;
+    if (d->cfg.sf == 7) {
+        switch (k1_variant()) {
+        case 1: return launch_k1_warp7<8, 3>(d, iq, n, bins, mags, st);
+        case 2: return launch_k1_warp7<12, 2>(d, iq, n, bins, mags, st);
+        case 3: return launch_k1_warp7<13, 2>(d, iq, n, bins, mags, st);
+        case 4: return launch_k1_warp7<9, 3>(d, iq, n, bins, mags, st);
+        default: break;
+        }
+    }
     switch (d->cfg.sf) {
     case 7: return launch_k1<7>(d, iq, n, bins, mags, st);
     case 8: return launch_k1<8>(d, iq, n, bins, mags, st);
