@@ -347,13 +347,15 @@ rx_stream_kernel(RxParams p) {
                     using C = K1Cfg<SF>;
                     K1Args a{x, p.down, p.tw, 1};
                     unsigned long long best = 0ull;
+                    float2 wtab[C::NP / C::TPS];
+                    k1_combine_twiddles<SF>(a, tid, wtab);
                     for (int s = 0; s < C::S; s++) {
                         k1_pass0<SF, false>(a, 0, s, tid, rx_dyn_smem);
                         __syncthreads();
                         k1_pass<SF, C::R1, C::SIG1>(a, tid, rx_dyn_smem);
                         __syncthreads();
                         if (C::R2 > 1) { k1_pass<SF, (C::R2 > 1 ? C::R2 : 2), 1>(a, tid, rx_dyn_smem); __syncthreads(); }
-                        unsigned long long k = tid < C::TPS ? k1_combine<SF>(a, s, tid, rx_dyn_smem) : 0ull;
+                        unsigned long long k = tid < C::TPS ? k1_combine<SF>(a, s, tid, rx_dyn_smem, wtab) : 0ull;
                         best = k > best ? k : best;
                         __syncthreads();
                     }
