@@ -247,10 +247,8 @@ def main():
 
     # ---- init-time table broadcast (the only collective on this path) -------------------------
     if world > 1:
-        view = torch.as_tensor(dec.tables_device_view(), device=device)
-        dist.broadcast(view, src=0)
-        torch.cuda.synchronize()
-        dec.tables_commit()
+        from gr_lora_b200 import sharding
+        sharding.broadcast_tables(dec, dist, device=device, src=0)
 
     iq, vals = synth_batch(torch, sf, args.channels, args.symbols_per_channel, args.snr_db, device, SEED + rank)
     bins = torch.empty(n_sym_total, dtype=torch.int32, device=device)
@@ -387,7 +385,8 @@ def main():
                        "l2": "inputs (8 GiB) larger than L2, no flush needed", "parallelism": f"streams sharded x{world}",
                        "demod_accuracy_vs_tx": acc},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": f"k1_fft_kernel<{sf}>",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "k1_sf7_warp_kernel<12,2>" if sf == 7 and os.environ.get("LORA_B200_K1", "w12x2") == "w12x2" else f"k1_fft_kernel<{sf}>",
                          "algorithmic_bytes_per_launch": int(abytes)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
         }
