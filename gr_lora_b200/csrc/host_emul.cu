@@ -3,6 +3,7 @@
 // on the host and compare them with the oracle.  Not part of liblora_b200.so.
 #include "k1_fft.cuh"
 #include "k1_warp.cuh"
+#include "k1_group.cuh"
 #include "int_chain.cuh"
 
 extern "C" {
@@ -25,6 +26,17 @@ int lb_k1_emulate(int sf, const float2 *x, size_t n_symbols, const float2 *chirp
 int lb_k1_emulate_warp_sf7(const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
     lb::K1Args a{x, chirp, tw, n_symbols};
     lb::w7_emulate(a, bins, mags);
+    return 0;
+}
+
+int lb_k1_emulate_group(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
+    lb::K1Args a{x, chirp, tw, n_symbols};
+    switch (sf) {
+    case 7: lb::g_emulate<7>(a, bins, mags); break;
+    case 8: lb::g_emulate<8>(a, bins, mags); break;
+    case 9: lb::g_emulate<9>(a, bins, mags); break;
+    default: return -1;
+    }
     return 0;
 }
 

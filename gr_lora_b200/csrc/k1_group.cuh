@@ -1,0 +1,283 @@
+// k1_group.cuh -- K1 for SF8 / SF9: a GROUP of W = 2^(SF-7) warps per symbol.
+//
+// The SF7 warp kernel (k1_warp.cuh) generalised: the T = 32 W threads of a group own a ring of TMA-fed
+// shared-memory slots (one symbol = 8*sps bytes each) and run, per symbol,
+//   pass 0   float4 #t of each of the 16 rows -> dechirp -> two radix-16 DIF FFTs in registers,
+//            inter-pass twiddle u^kc (u = W_N^a lane invariant, powers kept in registers)
+//   exch 1   XOR-swizzled 128-bit exchange through the consumed slot: thread (kc, h) receives its
+//            NR = 4/W polyphase branches of output column kc, all M0 = 8 W points
+//   pass 1   NR radix-M0 FFTs in registers (radix 16 at SF8, radix 32 at SF9)
+//   exch 2   second swizzled exchange ([bin][branch]) so that each thread holds all 8 branches of 4 bins
+//   combine  Horner over the 8 branches with ONE lane-invariant twiddle per bin, |.|^2, group argmax
+// Same arithmetic as get_shift_fft (lib/decoder_impl.cc:430-464); see k1_fft.cuh for the derivation.
+// Shared-memory traffic per symbol: 6 x 8*sps bytes (slot read, chirp read, two exchanges).
+#pragma once
+#include "k1_warp.cuh"
+
+namespace lb {
+
+template <int SF>
+struct GCfg {
+    static constexpr int W = 1 << (SF - 7);          // warps per group
+    static constexpr int T = 32 * W;                 // threads per group
+    static constexpr int N = 1 << SF, SPS = 8 * N;
+    static constexpr int M0 = 8 * W;                 // points of the second FFT (columns)
+    static constexpr int NR = 4 / W;                 // branches per thread in pass 1: 4, 2, 1
+    static constexpr int LPK = 2 * W;                // lanes per output column kc
+    static constexpr int SLOT_F4 = 16 * T;           // float4 per slot
+    static constexpr uint32_t SLOT_BYTES = 8u * SPS;
+    static_assert(SF >= 7 && SF <= 9, "group kernel: SF7..SF9");
+};
+
+template <int SF> LB_HD int g_swz1(int kc) { return SF == 7 ? ((kc & 1) | ((kc & 2) << 1)) : ((kc & 1) << 2); }
+template <int SF> LB_HD int g_signed_bin(int q) { return q < GCfg<SF>::N / 2 ? q : q - GCfg<SF>::N; }
+
+template <int SF>
+struct GConsts {
+    float2 twk[16];          // W_N^{a kc}, a = t >> 2 (pass-0 output twiddle), twk[0] = 1
+    float2 wq[4];            // W_sps^{q'} for the thread's bins q = t + T i
+};
+
+template <int SF>
+LB_HD void g_consts(int t, const float2 *tw, GConsts<SF> &c) {
+    using C = GCfg<SF>;
+    const int a = t >> 2;
+    for (int kc = 0; kc < 16; kc++) c.twk[kc] = k1_ld_table(tw + ((a * kc * 8) & (C::SPS - 1)));     // W_N = W_sps^8
+    for (int i = 0; i < 4; i++) c.wq[i] = k1_ld_table(tw + (g_signed_bin<SF>(t + C::T * i) & (C::SPS - 1)));
+}
+
+// pass 0 + exchange-1 write.  slot/chirp: natural sample order as float4 pairs.
+template <int SF>
+LB_HD void g_pass0(int t, const float4 *slot, const float4 *chirp, const GConsts<SF> &c, float2 *v0, float2 *v1) {
+    using C = GCfg<SF>;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        const float4 xv = slot[r * C::T + t];
+        const float4 dv = chirp[r * C::T + t];
+        v0[r] = cmul(make_float2(xv.x, xv.y), make_float2(dv.x, dv.y));
+        v1[r] = cmul(make_float2(xv.z, xv.w), make_float2(dv.z, dv.w));
+    }
+    dft_dif<16>(v0);
+    dft_dif<16>(v1);
+#pragma unroll
+    for (int kc = 1; kc < 16; kc++) {
+        const int br = bitrev<16>(kc);
+        v0[br] = cmul(v0[br], c.twk[kc]);
+        v1[br] = cmul(v1[br], c.twk[kc]);
+    }
+}
+
+template <int SF>
+LB_HD void g_store1(int t, float4 *slot, const float2 *v0, const float2 *v1) {
+    using C = GCfg<SF>;
+#pragma unroll
+    for (int kc = 0; kc < 16; kc++) {
+        const int br = bitrev<16>(kc);
+        slot[kc * C::T + (t ^ g_swz1<SF>(kc))] = make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y);
+    }
+}
+
+// pass 1: thread (kc = t / LPK, h = t % LPK) loads branches r = h*NR .. h*NR+NR-1, all M0 columns,
+// and runs NR radix-M0 FFTs.  g[i][bitrev(ka)] = G_{h NR + i}[kc + 16 ka].
+template <int SF>
+LB_HD void g_pass1(int t, const float4 *slot, float2 (*g)[GCfg<SF>::M0]) {
+    using C = GCfg<SF>;
+    const int kc = t / C::LPK, h = t % C::LPK;
+    const int sw = g_swz1<SF>(kc);
+    const float4 *row = slot + kc * C::T;
+#pragma unroll
+    for (int a = 0; a < C::M0; a++) {
+        if constexpr (C::NR == 4) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const float4 u = row[(4 * a + 2 * h + e) ^ sw];
+                g[2 * e][a] = make_float2(u.x, u.y);
+                g[2 * e + 1][a] = make_float2(u.z, u.w);
+            }
+        } else if constexpr (C::NR == 2) {
+            const float4 u = row[(4 * a + h) ^ sw];
+            g[0][a] = make_float2(u.x, u.y);
+            g[C::NR - 1][a] = make_float2(u.z, u.w);
+        } else {
+            const float2 *p2 = reinterpret_cast<const float2 *>(row + ((4 * a + (h >> 1)) ^ sw));
+            g[0][a] = p2[h & 1];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < C::NR; i++) dft_dif<C::M0>(g[i]);
+}
+
+// exchange 2: [bin q][16-byte unit u = r/2], unit position XOR ((q >> 1) & 3); 4 units (64 B) per bin
+LB_HD int g_unit2(int q, int u) { return q * 4 + (u ^ ((q >> 1) & 3)); }
+
+template <int SF>
+LB_HD void g_store2(int t, float4 *slot, float2 (*g)[GCfg<SF>::M0]) {
+    using C = GCfg<SF>;
+    const int kc = t / C::LPK, h = t % C::LPK;
+#pragma unroll
+    for (int ka = 0; ka < C::M0; ka++) {
+        const int br = bitrev<C::M0>(ka);
+        const int q = kc + 16 * ka;
+        if constexpr (C::NR == 4) {
+            slot[g_unit2(q, 2 * h)] = make_float4(g[0][br].x, g[0][br].y, g[1][br].x, g[1][br].y);
+            slot[g_unit2(q, 2 * h + 1)] = make_float4(g[2][br].x, g[2][br].y, g[3][br].x, g[3][br].y);
+        } else if constexpr (C::NR == 2) {
+            slot[g_unit2(q, h)] = make_float4(g[0][br].x, g[0][br].y, g[C::NR - 1][br].x, g[C::NR - 1][br].y);
+        } else {
+            float2 *p2 = reinterpret_cast<float2 *>(slot + g_unit2(q, h >> 1));
+            p2[h & 1] = g[0][br];
+        }
+    }
+}
+
+// combine: bins q = t + T i, i = 0..3: all 8 branches, Horner with w = W_sps^{q'}
+template <int SF>
+LB_HD unsigned long long g_combine(int t, const float4 *slot, const GConsts<SF> &c) {
+    using C = GCfg<SF>;
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int q = t + C::T * i;
+        float2 gv[8];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float4 v = slot[g_unit2(q, u)];
+            gv[2 * u] = make_float2(v.x, v.y);
+            gv[2 * u + 1] = make_float2(v.z, v.w);
+        }
+        const float2 w = c.wq[i];
+        float2 acc = gv[7];
+#pragma unroll
+        for (int r = 6; r >= 0; r--) acc = cfma(acc, w, gv[r]);
+        if (q == C::N / 2) {                             // tmp[N/2] += F[N/2]  (:450); thread 0, i = 2
+            const float2 wc = cconj(w);
+            float2 acc2 = gv[7];
+#pragma unroll
+            for (int r = 6; r >= 0; r--) acc2 = cfma(acc2, wc, gv[r]);
+            acc = cadd(acc, acc2);
+        }
+        const unsigned long long key = pack_key(cnorm2(acc), (uint32_t)q);
+        best = key > best ? key : best;
+    }
+    return best;
+}
+
+#ifdef __CUDACC__
+template <int SF, int NGROUPS, int NSLOT>
+struct GSmem {
+    float4 chirp[GCfg<SF>::SLOT_F4];
+    float4 slots[NGROUPS][NSLOT][GCfg<SF>::SLOT_F4];
+    uint64_t bars[NGROUPS][NSLOT];
+    unsigned long long keys[NGROUPS][GCfg<SF>::W];
+};
+
+LB_D void group_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <int SF, int NGROUPS, int NSLOT>
+__global__ void __launch_bounds__(NGROUPS * GCfg<SF>::T, 1)
+k1_group_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags) {
+    using C = GCfg<SF>;
+    extern __shared__ __align__(128) unsigned char g_raw[];
+    GSmem<SF, NGROUPS, NSLOT> &sm = *reinterpret_cast<GSmem<SF, NGROUPS, NSLOT> *>(g_raw);
+    const int grp = threadIdx.x / C::T, t = threadIdx.x % C::T;
+    const int lane = t & 31, wig = t >> 5;              // warp in group
+    const int bar_id = 1 + grp;                         // named barrier of this group (0 = __syncthreads)
+    const size_t gg = (size_t)blockIdx.x * NGROUPS + grp, g_total = (size_t)gridDim.x * NGROUPS;
+
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) mbar_init(&sm.bars[grp][s], 1);
+        fence_mbar_init();
+    }
+    for (int i = threadIdx.x; i < C::SLOT_F4; i += NGROUPS * C::T) sm.chirp[i] = k1_ld_table4(a.chirp + 2 * i);
+    __syncthreads();
+    if (t == 0) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) {
+            const size_t sym = gg + (size_t)s * g_total;
+            if (sym < a.n_symbols) {
+                mbar_expect_tx(&sm.bars[grp][s], C::SLOT_BYTES);
+                bulk_g2s(sm.slots[grp][s], a.x + sym * C::SPS, C::SLOT_BYTES, &sm.bars[grp][s]);
+            }
+        }
+    }
+    GConsts<SF> c;
+    g_consts<SF>(t, a.tw, c);
+
+    uint32_t it = 0;
+    for (size_t sym = gg; sym < a.n_symbols; sym += g_total, it++) {
+        const int s = it % NSLOT;
+        const uint32_t parity = (it / NSLOT) & 1u;
+        float4 *slot = sm.slots[grp][s];
+        mbar_wait(&sm.bars[grp][s], parity);
+        {
+            float2 v0[16], v1[16];
+            g_pass0<SF>(t, slot, sm.chirp, c, v0, v1);
+            group_bar(bar_id, C::T);                    // everyone has read the slot
+            g_store1<SF>(t, slot, v0, v1);
+        }
+        group_bar(bar_id, C::T);
+        float2 g[C::NR][C::M0];
+        g_pass1<SF>(t, slot, g);
+        group_bar(bar_id, C::T);                        // exchange-1 reads done
+        g_store2<SF>(t, slot, g);
+        group_bar(bar_id, C::T);
+        unsigned long long best = g_combine<SF>(t, slot, c);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+            best = o > best ? o : best;
+        }
+        if (lane == 0) sm.keys[grp][wig] = best;
+        group_bar(bar_id, C::T);                        // exchange-2 reads done + keys visible
+        if (t == 0) {
+            const size_t nxt = sym + (size_t)NSLOT * g_total;
+            if (nxt < a.n_symbols) {
+                fence_proxy_async();
+                mbar_expect_tx(&sm.bars[grp][s], C::SLOT_BYTES);
+                bulk_g2s(slot, a.x + nxt * C::SPS, C::SLOT_BYTES, &sm.bars[grp][s]);
+            }
+            unsigned long long bb = sm.keys[grp][0];
+#pragma unroll
+            for (int k = 1; k < C::W; k++) bb = sm.keys[grp][k] > bb ? sm.keys[grp][k] : bb;
+            bins[sym] = key_idx(bb);
+            if (mags) mags[sym] = sqrtf(key_mag2(bb));
+        }
+        // keys[] is rewritten only after four more group barriers: no hazard with thread 0's read
+    }
+}
+#endif  // __CUDACC__
+
+// ---- CPU emulation ---------------------------------------------------------------------------
+template <int SF>
+inline void g_emulate(const K1Args &a, uint32_t *bins, float *mags) {
+    using C = GCfg<SF>;
+    float4 *slot = new float4[C::SLOT_F4];
+    float4 *chirp = new float4[C::SLOT_F4];
+    GConsts<SF> *c = new GConsts<SF>[C::T];
+    for (int t = 0; t < C::T; t++) g_consts<SF>(t, a.tw, c[t]);
+    for (int i = 0; i < C::SLOT_F4; i++) chirp[i] = make_float4(a.chirp[2 * i].x, a.chirp[2 * i].y, a.chirp[2 * i + 1].x, a.chirp[2 * i + 1].y);
+    auto v0 = new float2[C::T][16];
+    auto v1 = new float2[C::T][16];
+    auto g = new float2[C::T][C::NR][C::M0];
+    for (size_t sym = 0; sym < a.n_symbols; sym++) {
+        const float2 *x = a.x + sym * C::SPS;
+        for (int i = 0; i < C::SLOT_F4; i++) slot[i] = make_float4(x[2 * i].x, x[2 * i].y, x[2 * i + 1].x, x[2 * i + 1].y);
+        for (int t = 0; t < C::T; t++) g_pass0<SF>(t, slot, chirp, c[t], v0[t], v1[t]);
+        for (int i = 0; i < C::SLOT_F4; i++) slot[i] = make_float4(NAN, NAN, NAN, NAN);
+        for (int t = 0; t < C::T; t++) g_store1<SF>(t, slot, v0[t], v1[t]);
+        for (int t = 0; t < C::T; t++) g_pass1<SF>(t, slot, g[t]);
+        for (int i = 0; i < C::SLOT_F4; i++) slot[i] = make_float4(NAN, NAN, NAN, NAN);
+        for (int t = 0; t < C::T; t++) g_store2<SF>(t, slot, g[t]);
+        unsigned long long best = 0ull;
+        for (int t = 0; t < C::T; t++) {
+            const unsigned long long k = g_combine<SF>(t, slot, c[t]);
+            best = k > best ? k : best;
+        }
+        bins[sym] = key_idx(best);
+        if (mags) mags[sym] = sqrtf(key_mag2(best));
+    }
+    delete[] slot; delete[] chirp; delete[] c; delete[] v0; delete[] v1; delete[] g;
+}
+
+}  // namespace lb

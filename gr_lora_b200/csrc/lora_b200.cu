@@ -5,6 +5,7 @@
 #include "../../include/lora_b200.h"
 #include "k1_fft.cuh"
 #include "k1_warp.cuh"
+#include "k1_group.cuh"
 #include "rx_stream.cuh"
 
 #include <algorithm>
@@ -208,6 +209,23 @@ int launch_k1_warp7(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, ui
     return LORA_B200_OK;
 }
 
+// SF8/SF9 (and SF7 as a cross-check): a group of 2^(SF-7) warps per symbol (k1_group.cuh)
+template <int SF, int NGROUPS, int NSLOT>
+int launch_k1_group(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(GSmem<SF, NGROUPS, NSLOT>);
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_group_kernel<SF, NGROUPS, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    const int grid = (int)std::min<size_t>((n_symbols + NGROUPS - 1) / NGROUPS, (size_t)d->n_sms);
+    k1_group_kernel<SF, NGROUPS, NSLOT><<<grid, NGROUPS * GCfg<SF>::T, smem, st>>>(a, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
     static int v = -1;
     if (v < 0) {
@@ -219,6 +237,7 @@ int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 
             else if (!strcmp(e, "w12x2")) v = 2;
             else if (!strcmp(e, "w13x2")) v = 3;
             else if (!strcmp(e, "w9x3")) v = 4;
+            else if (!strcmp(e, "group")) v = 5;
         }
     }
     return v;
@@ -233,8 +252,13 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
         case 2: return launch_k1_warp7<12, 2>(d, iq, n, bins, mags, st);
         case 3: return launch_k1_warp7<13, 2>(d, iq, n, bins, mags, st);
         case 4: return launch_k1_warp7<9, 3>(d, iq, n, bins, mags, st);
+        case 5: return launch_k1_group<7, 12, 2>(d, iq, n, bins, mags, st);
         default: break;
         }
+    }
+    if (k1_variant() != 0) {
+        if (d->cfg.sf == 8) return launch_k1_group<8, 6, 2>(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 9) return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
     }
     switch (d->cfg.sf) {
     case 7: return launch_k1<7>(d, iq, n, bins, mags, st);

@@ -18,6 +18,8 @@ GOLD = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text()
 def emul():
     L = C.CDLL(str(B.build_host_emul()))
     L.lb_k1_emulate.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lb_k1_emulate_warp_sf7.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lb_k1_emulate_group.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lb_emul_decode.restype = C.c_uint32
     L.lb_emul_decode.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_uint32]
     L.lb_emul_deinterleave.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
@@ -48,6 +50,31 @@ def test_k1_emulation_matches_oracle(emul, oracle, sf):
     assert np.array_equal(bins, ob)
     assert [int(b) for b in bins] == g["fft_bins"]
     np.testing.assert_allclose(mags, om, rtol=1e-5)
+
+
+@pytest.mark.parametrize("which", ["warp7", "group7", "group8", "group9"])
+def test_k1_fast_kernels_emulation_matches_oracle(emul, oracle, which):
+    """k1_warp.cuh (SF7, warp per symbol) and k1_group.cuh (SF7-9, group per symbol): lane/thread
+    functions run on the host; bins must equal the oracle on the fixture, the edge bins and on noise."""
+    from golden.make_golden import k1_case
+    sf = int(which[-1])
+    g = GOLD["k1"][str(sf)]
+    vals, x = k1_case(sf, g["n"], g["snr_db"], g["seed"])
+    rng = np.random.default_rng(77)
+    d = oracle.Decoder(sf=sf)
+    noise = (rng.standard_normal(9 * d.sps) + 1j * rng.standard_normal(9 * d.sps)).astype(np.complex64)
+    chirp, tw = d.downchirp, twiddle_table(d.sps)
+    for sig in (x, noise):
+        n = sig.size // d.sps
+        bins, mags = np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        if which == "warp7":
+            emul.lb_k1_emulate_warp_sf7(sig.ctypes.data, n, chirp.ctypes.data, tw.ctypes.data, bins.ctypes.data, mags.ctypes.data)
+        else:
+            assert emul.lb_k1_emulate_group(sf, sig.ctypes.data, n, chirp.ctypes.data, tw.ctypes.data, bins.ctypes.data, mags.ctypes.data) == 0
+        ob, om = d.demod_fft_batch(sig)
+        assert np.array_equal(bins, ob)
+        np.testing.assert_allclose(mags, om, rtol=1e-5)
+    assert [int(b) for b in ob] != []
 
 
 def test_k1_emulation_ragged_batch_and_noise_only(emul, oracle):
