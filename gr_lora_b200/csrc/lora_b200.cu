@@ -6,6 +6,7 @@
 #include "k1_fft.cuh"
 #include "k1_warp.cuh"
 #include "k1_group.cuh"
+#include "k1_cluster.cuh"
 #include "rx_stream.cuh"
 
 #include <algorithm>
@@ -226,6 +227,46 @@ int launch_k1_group(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, ui
     return LORA_B200_OK;
 }
 
+// SF11/SF12: one cluster of 2/4 CTAs per symbol, pass 0 scattered over DSMEM (k1_cluster.cuh)
+template <int SF>
+int launch_k1_cluster(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    using C = K1Cfg<SF>;
+    using K = KCfg<SF>;
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(float2) * C::SMEM_ELEMS;
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_cluster_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    if (d->packed_cap < n_symbols) {
+        if (d->d_packed) cudaFree(d->d_packed);
+        d->d_packed = nullptr; d->packed_cap = 0;
+        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
+        d->packed_cap = n_symbols;
+    }
+    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    size_t n_clusters = std::min<size_t>(n_symbols, (size_t)(d->n_sms * 2) / K::CL);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * K::CL));
+    cfg.blockDim = dim3(K1_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = K::CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k1_cluster_kernel<SF>, a, d->d_packed));
+    d->launches++;
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
     static int v = -1;
     if (v < 0) {
@@ -259,6 +300,8 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
     if (k1_variant() != 0) {
         if (d->cfg.sf == 8) return launch_k1_group<8, 6, 2>(d, iq, n, bins, mags, st);
         if (d->cfg.sf == 9) return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 11) return launch_k1_cluster<11>(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 12) return launch_k1_cluster<12>(d, iq, n, bins, mags, st);
     }
     switch (d->cfg.sf) {
     case 7: return launch_k1<7>(d, iq, n, bins, mags, st);
