@@ -279,6 +279,8 @@ int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 
             else if (!strcmp(e, "w13x2")) v = 3;
             else if (!strcmp(e, "w9x3")) v = 4;
             else if (!strcmp(e, "group")) v = 5;
+            else if (!strcmp(e, "w10x2")) v = 6;
+            else if (!strcmp(e, "w11x2")) v = 7;
         }
     }
     return v;
@@ -294,6 +296,8 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
         case 3: return launch_k1_warp7<13, 2>(d, iq, n, bins, mags, st);
         case 4: return launch_k1_warp7<9, 3>(d, iq, n, bins, mags, st);
         case 5: return launch_k1_group<7, 12, 2>(d, iq, n, bins, mags, st);
+        case 6: return launch_k1_warp7<10, 2>(d, iq, n, bins, mags, st);
+        case 7: return launch_k1_warp7<11, 2>(d, iq, n, bins, mags, st);
         default: break;
         }
     }

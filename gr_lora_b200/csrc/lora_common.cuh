@@ -14,17 +14,52 @@
 
 namespace lb {
 
+// ---- complex arithmetic ---------------------------------------------------------------------
+// On the device every complex value lives in an aligned 64-bit register pair and the arithmetic uses
+// Blackwell's packed fp32 instructions (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2,
+// sm_100+).  They have the FLOP rate of the scalar ops but need half the issue slots, and the K1
+// kernels are issue bound (profiles/r1_k1_sf7_warp.md, profiles/r1_f32x2_tput.txt).  ptxas folds the
+// scalar broadcasts {x,x}, the pair swaps {y,x} and whole-pair negations below into operand modifiers
+// (R.F32, .LO_HI, -R), so a complex multiply-add is two instructions.  The host build (CPU emulation
+// of the kernels for the non-GPU tests) uses the plain scalar formulas.
+#ifdef __CUDA_ARCH__
+typedef unsigned long long lb_u64;
+LB_D lb_u64 pk2(float lo, float hi) { lb_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+LB_D float2 up2(lb_u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+LB_D lb_u64 add2(lb_u64 a, lb_u64 b) { lb_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+LB_D lb_u64 sub2(lb_u64 a, lb_u64 b) { lb_u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+LB_D lb_u64 mul2(lb_u64 a, lb_u64 b) { lb_u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+LB_D lb_u64 fma2(lb_u64 a, lb_u64 b, lb_u64 c) { lb_u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+LB_D float2 cadd(float2 a, float2 b) { return up2(add2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+LB_D float2 csub(float2 a, float2 b) { return up2(sub2(pk2(a.x, a.y), pk2(b.x, b.y))); }
+// packed product with a compile-time constant (used inside the radix butterflies)
+LB_D float2 cmul_const(float2 a, float wx, float wy) {
+    return up2(fma2(pk2(a.x, a.x), pk2(wx, wy), mul2(pk2(a.y, a.y), pk2(-wy, wx))));
+}
+#ifdef LB_PACKED_CMUL
+// plain complex product (the reference multiplies by the down-chirp, not its conjugate,
+// lib/decoder_impl.cc:436-438):  a*b = a.x*(b.x, b.y) + a.y*(-b.y, b.x)
+LB_D float2 cmul(float2 a, float2 b) {
+    return up2(fma2(pk2(a.x, a.x), pk2(b.x, b.y), mul2(pk2(a.y, a.y), pk2(-b.y, b.x))));
+}
+// a * w + c
+LB_D float2 cfma(float2 a, float2 w, float2 c) {
+    return up2(fma2(pk2(a.x, a.x), pk2(w.x, w.y), fma2(pk2(a.y, a.y), pk2(-w.y, w.x), pk2(c.x, c.y))));
+}
+LB_D float cnorm2(float2 a) { const float2 q = up2(mul2(pk2(a.x, a.y), pk2(a.x, a.y))); return q.x + q.y; }
+#endif
+#else
 LB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 LB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-// plain complex product (the reference multiplies by the down-chirp, not its conjugate,
-// lib/decoder_impl.cc:436-438)
+#endif
+#if !defined(__CUDA_ARCH__) || !defined(LB_PACKED_CMUL)
 LB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-// a * w + c
 LB_HD float2 cfma(float2 a, float2 w, float2 c) {
     return make_float2(fmaf(a.x, w.x, fmaf(-a.y, w.y, c.x)), fmaf(a.x, w.y, fmaf(a.y, w.x, c.y)));
 }
-LB_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 LB_HD float cnorm2(float2 a) { return fmaf(a.x, a.x, a.y * a.y); }
+#endif
+LB_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 
 // cos/sin(2*pi*e/32), e = 0..15, as literals so that they fold after unrolling
 LB_HD float cos32(int e) {
@@ -52,6 +87,11 @@ LB_HD float sin32(int e) { return cos32(e > 8 ? e - 8 : 8 - e); }
 
 // multiply by W_32^e = exp(-2*pi*i*e/32), e in [0,16), e known at compile time after unrolling
 LB_HD float2 mul_w32(float2 a, int e) {
+#ifdef __CUDA_ARCH__
+    if (e == 0) return a;
+    if (e == 8) return up2(mul2(pk2(a.y, a.x), pk2(1.0f, -1.0f)));          // * (-i): swap + one sign
+    return cmul_const(a, cos32(e), -sin32(e));                               // W = c - i s
+#else
     const float h = 0.70710678118654757f;
     switch (e) {
     case 0: return a;
@@ -65,6 +105,7 @@ LB_HD float2 mul_w32(float2 a, int e) {
         return make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s));
     }
     }
+#endif
 }
 
 // in-register radix-2 DIF DFT of R points (forward, e^{-j}); X[k] ends up at v[bitrev(k)]
