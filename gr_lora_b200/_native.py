@@ -58,6 +58,16 @@ SIGNATURES = {
     "lora_b200_stdout_last": (_i, [_vp, _u32, C.c_char_p, _sz]),
     "lora_b200_trace_read": (_i, [_vp, _u32, C.POINTER(Step), _sz, C.POINTER(_sz)]),
     "lora_b200_launch_count": (C.c_uint64, [_vp]),
+    "lora_b200_channelizer_create": (_vp, [C.c_float, C.c_float, C.POINTER(C.c_float), _u32, _u32, _u32, C.c_int32]),
+    "lora_b200_channelizer_destroy": (None, [_vp]),
+    "lora_b200_channelizer_last_error": (C.c_char_p, []),
+    "lora_b200_channelizer_ntaps": (_u32, [_vp]),
+    "lora_b200_channelizer_taps": (_i, [_vp, C.POINTER(C.c_float), _sz]),
+    "lora_b200_channelizer_apply_cfo": (_i, [_vp, _u32, C.c_float]),
+    "lora_b200_channelizer_work_dev": (_i, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), _vp]),
+    "lora_b200_channelizer_work_host": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
+    "lora_b200_channelizer_output": (_vp, [_vp, _u32, C.POINTER(_sz)]),
+    "lora_b200_channelizer_launch_count": (C.c_uint64, [_vp]),
 }
 
 _lib = None

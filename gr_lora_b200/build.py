@@ -40,7 +40,7 @@ def _sources():
 def build(force: bool = False, verbose: bool = False) -> Path:
     if force or _stale(LIB, _sources()):
         flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-        cmd = [_nvcc(), *flags, "-o", str(LIB), str(CSRC / "lora_b200.cu")]
+        cmd = [_nvcc(), *flags, "-o", str(LIB), str(CSRC / "lora_b200.cu"), str(CSRC / "channelizer.cu")]
         if verbose:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)

@@ -1,8 +1,7 @@
 """Host-side mirror of the reference's ``lora_receiver`` hier block (python/lora_receiver.py:26-89):
 same constructor arguments, same wiring (optional conjugate -> channelizer -> decoder) and the
-same 'frames' message port, without GNU Radio.  The decoder is the GPU path; the channelizer
-(GNU Radio's freq_xlating_fir_filter_ccf inside lib/channelizer_impl.cc:40-60) is SURVEY.md 8f
-row N1 ("next") and is not built yet, so only already-channelised input is accepted."""
+same 'frames' message port, without GNU Radio.  Decoder and channelizer both run
+on the GPU; between them the IQ never leaves device memory."""
 from __future__ import annotations
 
 import numpy as np
@@ -18,10 +17,12 @@ class lora_receiver:
         self.decimation, self.conj = decimation, conj
         self.disable_channelization = disable_channelization
         self.disable_drift_correction = disable_drift_correction
-        needs_channelizer = not disable_channelization and (decimation != 1 or float(self.channel_list[0]) != float(center_freq))
-        if needs_channelizer:
-            raise NotImplementedError("channelizer (SURVEY.md 8f N1) is not built yet: feed channelised IQ "
-                                      "(channel_list[0] == center_freq, decimation == 1) or disable_channelization=True")
+        self.channelizer = None
+        if not disable_channelization:
+            # python/lora_receiver.py:52: lora.channelizer(samp_rate, center_freq, channel_list, bandwidth, decimation)
+            from .channelizer import channelizer
+            self.channelizer = channelizer(samp_rate, center_freq, self.channel_list, bandwidth, decimation,
+                                           device=decoder_kw.get("device", -1))
         if disable_channelization and decimation != 1:
             raise NotImplementedError("fractional_resampler_cc path (python/lora_receiver.py:58-61) is host plumbing, not built")
         # python/lora_receiver.py:53
@@ -37,10 +38,33 @@ class lora_receiver:
         return np.conj(x) if self.conj else x        # blocks.conjugate_cc, :50,:70-75
 
     def work(self, samples, stream=0):
-        return self.decoder.work(self._front(samples), stream)
+        if self.channelizer is None:
+            return self.decoder.work(self._front(samples), stream)
+        return self.run(samples, stream)
 
     def run(self, samples, stream=0):
-        return self.decoder.run(self._front(samples), stream)
+        """Whole capture through (channelizer ->) [conj ->] decoder.  With the channelizer the filtered IQ
+        stays in device memory: the decoder consumes the channelizer's output buffer directly.  Only
+        channel_list[0] reaches the decoder, as in the reference (lib/channelizer_impl.cc:47,56-57)."""
+        if self.channelizer is None:
+            return self.decoder.run(self._front(samples), stream)
+        if self.conj:
+            raise NotImplementedError("conj=True after the GPU channelizer is not wired (host conjugate needs the samples back)")
+        x = np.asarray(samples, dtype=np.complex64)
+        x = x[: (x.size // self.decimation) * self.decimation]
+        limit = int(self.decoder.cfg.max_items_per_call or (1 << 20))
+        pos_out, need = 0, 2 * self.decoder.sps
+        # the channelizer is stateful (history, rotator), so the capture is filtered once into one device
+        # buffer and the decoder walks over it call by call
+        n_out = self.channelizer.work(x)
+        ptr, stride = self.channelizer.output_ptr(0)
+        while n_out - pos_out >= need:
+            n = min(limit, n_out - pos_out)
+            c = int(self.decoder.work_batch(ptr + 8 * pos_out, n_items=n, stride_items=n, host=0)[0])
+            if c == 0:
+                break
+            pos_out += c
+        return pos_out * self.decimation
 
     def get_sf(self):
         return self.sf

@@ -157,6 +157,33 @@ int lora_b200_stdout_last(lora_b200_decoder *d, uint32_t stream, char *buf, size
 /* per-step trace of the last work call (needs trace_capacity > 0) */
 int lora_b200_trace_read(lora_b200_decoder *d, uint32_t stream, lora_b200_step *steps, size_t cap, size_t *n);
 
+/* ---- N1: the channelizer in front of the decoder -------------------------------------
+ * Replaces lora::channelizer::make(samp_rate, center_freq, channel_list, bandwidth, decimation)
+ * (include/lora/channelizer.h:49, lib/channelizer_impl.cc:40-60): GNU Radio's
+ * freq_xlating_fir_filter_ccf with firdes::low_pass(1, fs, bw/2 + 15000, 10000, Hamming) taps.  The
+ * reference wires only channel_list[0]; here every listed channel is produced by one FIR-bank launch:
+ * out[ch][n] for n < n_in / decimation (device pointers, async on cuda_stream).  Filter history and
+ * rotator phase carry over between calls like a GNU Radio block's. */
+typedef struct lora_b200_channelizer lora_b200_channelizer;
+lora_b200_channelizer *lora_b200_channelizer_create(float samp_rate, float center_freq, const float *channel_list,
+                                                    uint32_t n_channels, uint32_t bandwidth, uint32_t decimation,
+                                                    int32_t device);
+void lora_b200_channelizer_destroy(lora_b200_channelizer *c);
+const char *lora_b200_channelizer_last_error(void);
+uint32_t lora_b200_channelizer_ntaps(const lora_b200_channelizer *c);
+int lora_b200_channelizer_taps(const lora_b200_channelizer *c, float *out, size_t cap);
+/* channelizer_impl::apply_cfo (lib/channelizer_impl.cc:68-71), driven by the "cfo" control message
+ * (lib/controller_impl.cc:52-57) */
+int lora_b200_channelizer_apply_cfo(lora_b200_channelizer *c, uint32_t channel, float cfo);
+int lora_b200_channelizer_work_dev(lora_b200_channelizer *c, const void *in_dev, size_t n_in, void *out_dev,
+                                   size_t out_stride, size_t *n_out, void *cuda_stream);
+/* host entry: uploads `in_host`, filters into an internal device buffer; _output() returns the DEVICE
+ * pointer of one channel's n_out items (valid until the next call) so the decoder can consume it
+ * without a host round trip (lora_b200_work_batch(..., host_ptr = 0)). */
+int lora_b200_channelizer_work_host(lora_b200_channelizer *c, const void *in_host, size_t n_in, size_t *n_out);
+const void *lora_b200_channelizer_output(const lora_b200_channelizer *c, uint32_t channel, size_t *stride_items);
+uint64_t lora_b200_channelizer_launch_count(const lora_b200_channelizer *c);
+
 /* how many kernels this library has launched since creation (bench.py's gpu_launches) */
 uint64_t lora_b200_launch_count(const lora_b200_decoder *d);
 
