@@ -57,5 +57,24 @@ def build_host_emul(force: bool = False) -> Path:
     return HOST_EMUL
 
 
+SHIM = ROOT / "build" / "lora_shim_demo"
+
+
+def build_shim(force: bool = False) -> Path:
+    """The C++ drop-in body of gr::lora::decoder_impl (host/decoder_impl.cc) + a file-replay main,
+    compiled against host/gr_stub (GNU Radio is not installed here) and linked to liblora_b200.so."""
+    host = PKG / "host"
+    srcs = [host / "decoder_impl.cc", host / "shim_main.cc", host / "decoder_impl.h", host / "lora" / "decoder.h",
+            host / "gr_stub" / "gnuradio" / "sync_block.h", ROOT / "include" / "lora_b200.h"]
+    build()
+    if force or _stale(SHIM, srcs) or SHIM.stat().st_mtime < LIB.stat().st_mtime:
+        SHIM.parent.mkdir(exist_ok=True)
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-I", str(host / "gr_stub"), "-I", str(host), "-I",
+               str(ROOT / "include"), "-o", str(SHIM), str(host / "decoder_impl.cc"), str(host / "shim_main.cc"),
+               "-L", str(PKG), "-llora_b200", f"-Wl,-rpath,{PKG}"]
+        subprocess.run(cmd, check=True)
+    return SHIM
+
+
 if __name__ == "__main__":
     print(build(verbose=True))
