@@ -5,6 +5,7 @@
 #include "k1_warp.cuh"
 #include "k1_group.cuh"
 #include "k1_cluster.cuh"
+#include "k1_sf10.cuh"
 #include "int_chain.cuh"
 
 extern "C" {
@@ -36,6 +37,7 @@ int lb_k1_emulate_group(int sf, const float2 *x, size_t n_symbols, const float2 
     case 7: lb::g_emulate<7>(a, bins, mags); break;
     case 8: lb::g_emulate<8>(a, bins, mags); break;
     case 9: lb::g_emulate<9>(a, bins, mags); break;
+    case 10: lb::s10_emulate(a, bins, mags); break;
     case 11: lb::kc_emulate<11>(a, bins, mags); break;
     case 12: lb::kc_emulate<12>(a, bins, mags); break;
     default: return -1;

@@ -7,6 +7,7 @@
 #include "k1_warp.cuh"
 #include "k1_group.cuh"
 #include "k1_cluster.cuh"
+#include "k1_sf10.cuh"
 #include "rx_stream.cuh"
 
 #include <algorithm>
@@ -267,6 +268,22 @@ int launch_k1_cluster(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, 
     return LORA_B200_OK;
 }
 
+// SF10: one 256-thread group per symbol, two radix-32 passes (k1_sf10.cuh)
+int launch_k1_sf10(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(S10Smem<2>);
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_sf10_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    const int grid = (int)std::min<size_t>(n_symbols, (size_t)d->n_sms);
+    k1_sf10_kernel<2><<<grid, S10_T, smem, st>>>(a, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
     static int v = -1;
     if (v < 0) {
@@ -304,6 +321,7 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
     if (k1_variant() != 0) {
         if (d->cfg.sf == 8) return launch_k1_group<8, 6, 2>(d, iq, n, bins, mags, st);
         if (d->cfg.sf == 9) return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 10 && !getenv("LORA_B200_K1_SF10_GENERIC")) return launch_k1_sf10(d, iq, n, bins, mags, st);
         if (d->cfg.sf == 11) return launch_k1_cluster<11>(d, iq, n, bins, mags, st);
         // SF12: the 4-CTA cluster version measured slower (0.107) than the DIF-split version (0.129): keep the latter
         if (d->cfg.sf == 12 && getenv("LORA_B200_K1_SF12_CLUSTER")) return launch_k1_cluster<12>(d, iq, n, bins, mags, st);
