@@ -8,6 +8,7 @@
 #include "k1_group.cuh"
 #include "k1_cluster.cuh"
 #include "k1_sf10.cuh"
+#include "k1_big.cuh"
 #include "rx_stream.cuh"
 
 #include <algorithm>
@@ -284,6 +285,45 @@ int launch_k1_sf10(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uin
     return LORA_B200_OK;
 }
 
+// SF11/SF12: cluster of 2/4 TMA-fed groups per symbol (k1_big.cuh)
+template <int SF>
+int launch_k1_big(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    using B = BCfg<SF>;
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(BSmem<2>);
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_big_kernel<SF, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    if (d->packed_cap < n_symbols) {
+        if (d->d_packed) cudaFree(d->d_packed);
+        d->d_packed = nullptr; d->packed_cap = 0;
+        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
+        d->packed_cap = n_symbols;
+    }
+    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    const size_t n_clusters = std::max<size_t>(1, std::min<size_t>(n_symbols, (size_t)d->n_sms / B::CL));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * B::CL));
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = B::CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, k1_big_kernel<SF, 2>, a, d->d_packed));
+    d->launches++;
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
     static int v = -1;
     if (v < 0) {
@@ -322,6 +362,10 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
         if (d->cfg.sf == 8) return launch_k1_group<8, 6, 2>(d, iq, n, bins, mags, st);
         if (d->cfg.sf == 9) return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
         if (d->cfg.sf == 10 && !getenv("LORA_B200_K1_SF10_GENERIC")) return launch_k1_sf10(d, iq, n, bins, mags, st);
+        if (!getenv("LORA_B200_K1_NO_BIG")) {
+            if (d->cfg.sf == 11) return launch_k1_big<11>(d, iq, n, bins, mags, st);
+            if (d->cfg.sf == 12) return launch_k1_big<12>(d, iq, n, bins, mags, st);
+        }
         if (d->cfg.sf == 11) return launch_k1_cluster<11>(d, iq, n, bins, mags, st);
         // SF12: the 4-CTA cluster version measured slower (0.107) than the DIF-split version (0.129): keep the latter
         if (d->cfg.sf == 12 && getenv("LORA_B200_K1_SF12_CLUSTER")) return launch_k1_cluster<12>(d, iq, n, bins, mags, st);
