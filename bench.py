@@ -50,7 +50,9 @@ def parse_args():
     ap.add_argument("--channels", type=int, default=4096)
     ap.add_argument("--symbols-per-channel", type=int, default=256)
     ap.add_argument("--snr-db", type=float, default=10.0)
-    ap.add_argument("--all-sf", action="store_true", help="also report K1 for SF8..SF12 (extra keys, same batch bytes)")
+    ap.add_argument("--all-sf", action="store_true", default=True,
+                    help="also report K1 for SF8..SF12 under per_sf (default on: the metric is quoted per SF)")
+    ap.add_argument("--no-all-sf", dest="all_sf", action="store_false")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

@@ -359,8 +359,17 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
         }
     }
     if (k1_variant() != 0) {
-        if (d->cfg.sf == 8) return launch_k1_group<8, 6, 2>(d, iq, n, bins, mags, st);
-        if (d->cfg.sf == 9) return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
+        static const char *gv = getenv("LORA_B200_K1_GROUPS");        // tuning knob: "a" = fewer groups, deeper ring
+        if (d->cfg.sf == 8) {
+            if (gv && gv[0] == 'a') return launch_k1_group<8, 4, 3>(d, iq, n, bins, mags, st);
+            if (gv && gv[0] == 'b') return launch_k1_group<8, 5, 2>(d, iq, n, bins, mags, st);
+            return launch_k1_group<8, 6, 2>(d, iq, n, bins, mags, st);
+        }
+        if (d->cfg.sf == 9) {
+            if (gv && gv[0] == 'a') return launch_k1_group<9, 2, 3>(d, iq, n, bins, mags, st);
+            if (gv && gv[0] == 'b') return launch_k1_group<9, 2, 2>(d, iq, n, bins, mags, st);
+            return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
+        }
         if (d->cfg.sf == 10 && !getenv("LORA_B200_K1_SF10_GENERIC")) return launch_k1_sf10(d, iq, n, bins, mags, st);
         // k1_big (cluster of TMA-fed groups) measured 0.287 (SF11) / 0.130 (SF12): membar + lg_throttle stalls
         // around the two cluster barriers (profiles/r1_k1_big_sf11.md); the simpler kernels below are faster

@@ -244,7 +244,7 @@ def channel(frames, *, sf: int, fs: float = 1e6, gap_symbols: float = 4.0, lead_
 
     Silence is noise only (the implicit-header end-of-packet test needs the energy to drop,
     lib/decoder_impl.cc:861).  The tail is long enough for the decoder's 2*sps look-ahead."""
-    sps = int(fs / (125e3 / (1 << sf))) if True else 0
+    sps = int(fs / (125e3 / (1 << sf)))
     rng = np.random.default_rng(seed)
     parts = [np.zeros(int(lead_symbols * sps), dtype=np.complex128)]
     for k, f in enumerate(frames):

@@ -155,3 +155,26 @@ def test_set_sf_is_refused_like_the_reference(torch, capsys):
     assert "Setting the spreading factor during execution is currently not supported" in err
     assert "Setting the sample rate during execution is currently not supported" in err and dec.sps == 1024
     dec.close()
+
+
+@pytest.mark.parametrize("fs", [500e3, 2e6])
+def test_other_sample_rates_gradient_path(torch, oracle, fs):
+    """samp_rate / bandwidth != 8 (decimation 4 and 16): the gradient path is generic in sps
+    (lib/decoder_impl.cc:83-87); the FFT demodulator is refused there instead of silently falling back."""
+    import gr_lora_b200 as G
+    from gr_lora_b200 import tx
+    sf, cr = 7, 4
+    payload = bytes.fromhex("0badc0de1234")
+    fsy = tx.encode_frame(payload, sf, cr)
+    frame = tx.modulate_frame(fsy, sf, fs=fs)
+    x = tx.channel([frame] * 2, sf=sf, fs=fs, snr_db=40.0, seed=3)
+    od = oracle.Decoder(samp_rate=fs, sf=sf, cr=cr, crc=True)
+    oc, _ = od.run(x)
+    want = od.frames()
+    assert [f[18:24] for f in want] == [payload] * 2
+    dec = G.decoder(fs, 125000, sf, False, cr, True, quiet=True, max_items_per_call=x.size)
+    assert dec.sps == int(fs / 125e3) * 128 and dec.decim == int(fs / 125e3)
+    assert dec.work(x) == oc and [f for _, f in dec.frames] == want
+    dec.close()
+    with pytest.raises(RuntimeError, match="samp_rate/bandwidth == 8"):
+        G.decoder(fs, 125000, sf, False, cr, True, quiet=True, demod="fft")
