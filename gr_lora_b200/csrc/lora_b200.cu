@@ -66,7 +66,6 @@ struct lora_b200_decoder {
     int k2_grid = 0;
     // e2e host path
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
-    cudaEvent_t copy_events[2] = {nullptr, nullptr};
     void *d_chunk[2] = {nullptr, nullptr};
     void *h_chunk[2] = {nullptr, nullptr};
     uint32_t *d_chunk_bins[2] = {nullptr, nullptr};
@@ -85,10 +84,10 @@ struct lora_b200_decoder {
     uint32_t *d_trace_n = nullptr;
     float2 *d_stage = nullptr;            // [n_streams][max_items]
     float2 *h_stage = nullptr;            // pinned, same shape
+    size_t stage_cap = 0;                 // items
     std::vector<unsigned long long> h_consumed;
     std::vector<RxFrameOut> h_frames;
     std::vector<std::string> stdout_last;
-    std::vector<int> h_state;
     uint64_t launches = 0;
 };
 
@@ -270,7 +269,23 @@ int launch_k1_cluster(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, 
 }
 
 // SF10: one 256-thread group per symbol, two radix-32 passes (k1_sf10.cuh)
+int launch_k1_sf10b(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(S10SmemB);
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_sf10b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    const int grid = (int)std::min<size_t>(n_symbols, (size_t)d->n_sms * 2);
+    k1_sf10b_kernel<<<grid, S10_T, smem, st>>>(a, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int launch_k1_sf10(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    if (getenv("LORA_B200_K1_SF10B")) return launch_k1_sf10b(d, iq, n_symbols, bins, mags, st);
     static bool attr_set[64] = {};
     const size_t smem = sizeof(S10Smem<2>);
     if (!attr_set[d->device & 63]) {
@@ -603,7 +618,6 @@ void lora_b200_destroy(lora_b200_decoder *d) {
     cudaFree(d->d_tables); cudaFree(d->d_packed); cudaFree(d->d_k2_scratch);
     for (int i = 0; i < 2; i++) {
         if (d->copy_streams[i]) cudaStreamDestroy(d->copy_streams[i]);
-        if (d->copy_events[i]) cudaEventDestroy(d->copy_events[i]);
         cudaFree(d->d_chunk[i]); cudaFree(d->d_chunk_bins[i]); cudaFree(d->d_chunk_mags[i]);
         if (d->h_chunk[i]) cudaFreeHost(d->h_chunk[i]);
     }
@@ -699,7 +713,6 @@ int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symb
         d->chunk_symbols = std::max<size_t>(1, ((size_t)64 << 20) / sym_bytes);
         for (int i = 0; i < 2; i++) {
             CU(cudaStreamCreateWithFlags(&d->copy_streams[i], cudaStreamNonBlocking));
-            CU(cudaEventCreateWithFlags(&d->copy_events[i], cudaEventDisableTiming));
             CU(cudaMalloc(&d->d_chunk[i], d->chunk_symbols * sym_bytes));
             CU(cudaMalloc(&d->d_chunk_bins[i], d->chunk_symbols * sizeof(uint32_t)));
             CU(cudaMalloc(&d->d_chunk_mags[i], d->chunk_symbols * sizeof(float)));
@@ -771,11 +784,16 @@ int lora_b200_deinterleave_dev(lora_b200_decoder *d, const uint32_t *words, uint
     return LORA_B200_OK;
 }
 
-static int ensure_stage(lora_b200_decoder *d) {
-    if (d->d_stage) return LORA_B200_OK;
-    const size_t bytes = sizeof(float2) * (size_t)d->cfg.max_items_per_call * d->cfg.n_streams;
-    CU(cudaMalloc(&d->d_stage, bytes));
-    CU(cudaMallocHost(&d->h_stage, bytes));
+// pinned host + device staging for the host-pointer entry points; grows on demand (calls are synchronous,
+// so one buffer serves every stream of a single-stream work() call)
+static int ensure_stage(lora_b200_decoder *d, size_t items) {
+    if (items <= d->stage_cap) return LORA_B200_OK;
+    if (d->d_stage) cudaFree(d->d_stage);
+    if (d->h_stage) cudaFreeHost(d->h_stage);
+    d->d_stage = nullptr; d->h_stage = nullptr; d->stage_cap = 0;
+    CU(cudaMalloc(&d->d_stage, sizeof(float2) * items));
+    CU(cudaMallocHost(&d->h_stage, sizeof(float2) * items));
+    d->stage_cap = items;
     return LORA_B200_OK;
 }
 
@@ -787,13 +805,11 @@ int lora_b200_work(lora_b200_decoder *d, uint32_t stream, const void *iq_host, s
     if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;     // never read past what was staged
     *consumed = 0;
     if (n_items < 2 * (size_t)d->sps) return LORA_B200_OK;                             // output_multiple, :91
-    int rc = ensure_stage(d);
+    int rc = ensure_stage(d, n_items);
     if (rc) return rc;
-    float2 *h = d->h_stage + (size_t)stream * d->cfg.max_items_per_call;
-    float2 *dv = d->d_stage + (size_t)stream * d->cfg.max_items_per_call;
-    memcpy(h, iq_host, sizeof(float2) * n_items);
-    CU(cudaMemcpyAsync(dv, h, sizeof(float2) * n_items, cudaMemcpyHostToDevice, d->rx_stream));
-    return run_rx(d, dv, d->cfg.max_items_per_call, n_items, stream, 1, consumed, cb, user);
+    memcpy(d->h_stage, iq_host, sizeof(float2) * n_items);
+    CU(cudaMemcpyAsync(d->d_stage, d->h_stage, sizeof(float2) * n_items, cudaMemcpyHostToDevice, d->rx_stream));
+    return run_rx(d, d->d_stage, n_items, n_items, stream, 1, consumed, cb, user);
 }
 
 int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, size_t stride_items, int host_ptr,
@@ -807,12 +823,12 @@ int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, s
     size_t stride = stride_items;
     if (host_ptr) {
         if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;
-        int rc = ensure_stage(d);
+        int rc = ensure_stage(d, n_items * ns);
         if (rc) return rc;
-        CU(cudaMemcpy2DAsync(d->d_stage, sizeof(float2) * d->cfg.max_items_per_call, iq, sizeof(float2) * stride_items,
+        CU(cudaMemcpy2DAsync(d->d_stage, sizeof(float2) * n_items, iq, sizeof(float2) * stride_items,
                              sizeof(float2) * n_items, ns, cudaMemcpyHostToDevice, d->rx_stream));
         dv = d->d_stage;
-        stride = d->cfg.max_items_per_call;
+        stride = n_items;
     }
     return run_rx(d, dv, stride, n_items, 0, ns, consumed, cb, user);
 }
