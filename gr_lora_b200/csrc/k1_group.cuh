@@ -13,6 +13,7 @@
 // Shared-memory traffic per symbol: 6 x 8*sps bytes (slot read, chirp read, two exchanges).
 #pragma once
 #include "k1_warp.cuh"
+#include "k1_group_consts.h"
 
 namespace lb {
 
@@ -36,6 +37,8 @@ template <int SF>
 struct GConsts {
     float2 twk[16];          // W_N^{a kc}, a = t >> 2 (pass-0 output twiddle), twk[0] = 1
     float2 wq[4];            // W_sps^{q'} for the thread's bins q = t + T i
+    float2 wq2[4];           // wq^2 (Horner over branch PAIRS)
+    float2 wb;               // pair-twiddle base of this lane: W_sps^{kc} (times the upper-half factor at SF9)
 };
 
 template <int SF>
@@ -44,6 +47,23 @@ LB_HD void g_consts(int t, const float2 *tw, GConsts<SF> &c) {
     const int a = t >> 2;
     for (int kc = 0; kc < 16; kc++) c.twk[kc] = k1_ld_table(tw + ((a * kc * 8) & (C::SPS - 1)));     // W_N = W_sps^8
     for (int i = 0; i < 4; i++) c.wq[i] = k1_ld_table(tw + (g_signed_bin<SF>(t + C::T * i) & (C::SPS - 1)));
+    for (int i = 0; i < 4; i++) c.wq2[i] = k1_ld_table(tw + ((2 * g_signed_bin<SF>(t + C::T * i)) & (C::SPS - 1)));
+    {   // w[ka] = W_sps^{q'} with q = kc + 16 ka = wb * g_cc[ka]; at SF9 the odd lane of a pair owns ka >= M0/2:
+        // g_cc[ka] = g_cc[ka - M0/2] * W_sps^{16 M0/2 - N}, folded into its wb
+        const int kc = t / C::LPK, h = t % C::LPK;
+        int e = kc;
+        if (C::NR == 1 && (h & 1)) e += 16 * (C::M0 / 2) - C::N;
+        c.wb = k1_ld_table(tw + (e & (C::SPS - 1)));
+    }
+}
+
+template <int SF>
+LB_HD float2 g_cc(int ka) {
+#ifdef __CUDA_ARCH__
+    return SF == 8 ? g_cc8_dev[ka & 15] : g_cc9_dev[ka & 31];
+#else
+    return SF == 8 ? g_cc8_host[ka & 15] : g_cc9_host[ka & 31];
+#endif
 }
 
 // pass 0 + exchange-1 write.  slot/chirp: natural sample order as float4 pairs.
@@ -162,6 +182,91 @@ LB_HD unsigned long long g_combine(int t, const float4 *slot, const GConsts<SF> 
     return best;
 }
 
+// ---- pair variant (SF8, SF9): combine branch pairs BEFORE the second exchange ---------------------
+// P_pr[q] = G_{2pr}[q] + w[q] G_{2pr+1}[q].  SF8 (NR = 2): both branches are in the thread.  SF9 (NR = 1):
+// the partner lane t^1 holds the other branch; the even lane finishes ka < M0/2, the odd lane ka >= M0/2
+// (own = this lane's G, bit-reversed; other = what the partner sent for this lane's half).
+// Returns NP = M0 (SF8) or M0/2 (SF9) values P[j] for ka = j (+ M0/2 on odd SF9 lanes).
+// Pq = the same with the conjugate twiddle for the quirk bin q = N/2 (kc = 0, ka = M0/2), else 0.
+template <int SF> struct GPair { static constexpr int NP = GCfg<SF>::NR == 2 ? GCfg<SF>::M0 : GCfg<SF>::M0 / 2; };
+
+template <int SF>
+LB_HD void g_pair_sf8(int t, float2 (*g)[GCfg<SF>::M0], const GConsts<SF> &c, float2 *P, float2 &Pq) {
+    using C = GCfg<SF>;
+    const int kc = t / C::LPK;
+    Pq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int ka = 0; ka < C::M0; ka++) {
+        const int br = bitrev<C::M0>(ka);
+        const float2 od = cmul(g[C::NR - 1][br], g_cc<SF>(ka));
+        P[ka] = cfma(od, c.wb, g[0][br]);
+        if (ka == C::M0 / 2 && kc == 0) Pq = cfma(cmul(g[C::NR - 1][br], cconj(g_cc<SF>(ka))), cconj(c.wb), g[0][br]);
+    }
+}
+
+// SF9: keep[j]/other[j] for ka = j + (odd ? M0/2 : 0); even_part/odd_part by lane parity
+template <int SF>
+LB_HD void g_pair_sf9(int t, const float2 *keep, const float2 *recv, const GConsts<SF> &c, float2 *P, float2 &Pq) {
+    using C = GCfg<SF>;
+    const int kc = t / C::LPK, odd = t & 1;
+    Pq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < C::M0 / 2; j++) {
+        const float2 ev = odd ? recv[j] : keep[j];
+        const float2 od = odd ? keep[j] : recv[j];
+        const float2 odc = cmul(od, g_cc<SF>(j));
+        P[j] = cfma(odc, c.wb, ev);
+        if (j == 0 && kc == 0 && odd) Pq = cfma(cmul(od, cconj(g_cc<SF>(j))), cconj(c.wb), ev);   // ka = M0/2
+    }
+}
+
+// exchange 2 (pair variant): [bin q][pair pr] float2, 4 pairs = 32 B per bin, 16-byte unit XOR (q >> 2) & 1
+// (rows of the upper half, written by the odd lanes at SF9, take the other 64-byte half of the bank window)
+LB_HD int g_row2p(int q) { return q ^ (((q >> 8) & 1) << 1); }
+LB_HD int g_pos2p(int q, int pr) { return g_row2p(q) * 4 + ((((pr >> 1) ^ ((q >> 2) & 1)) << 1) | (pr & 1)); }
+
+template <int SF>
+LB_HD void g_store2p(int t, float2 *slot2, const float2 *P, float2 Pq, float2 *quirk) {
+    using C = GCfg<SF>;
+    const int kc = t / C::LPK, h = t % C::LPK;
+    const int pr = C::NR == 2 ? h : (h >> 1);
+    const int ka0 = (C::NR == 1 && (h & 1)) ? C::M0 / 2 : 0;
+#pragma unroll
+    for (int j = 0; j < GPair<SF>::NP; j++) slot2[g_pos2p(kc + 16 * (ka0 + j), pr)] = P[j];
+    if (kc == 0 && (C::NR == 2 || (h & 1))) quirk[pr] = Pq;
+}
+
+template <int SF>
+LB_HD unsigned long long g_combine_p(int t, const float2 *slot2, const float2 *quirk, const GConsts<SF> &c) {
+    using C = GCfg<SF>;
+    unsigned long long best = 0ull;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int q = t + C::T * i;
+        float2 pv[4];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const float4 v = *reinterpret_cast<const float4 *>(slot2 + g_row2p(q) * 4 + ((u ^ ((q >> 2) & 1)) << 1));
+            pv[2 * u] = make_float2(v.x, v.y);
+            pv[2 * u + 1] = make_float2(v.z, v.w);
+        }
+        const float2 w2 = c.wq2[i];
+        float2 acc = cfma(pv[3], w2, pv[2]);
+        acc = cfma(acc, w2, pv[1]);
+        acc = cfma(acc, w2, pv[0]);
+        if (q == C::N / 2) {                             // tmp[N/2] += F[N/2]  (:450)
+            const float2 wc = cconj(w2);
+            float2 a2 = cfma(quirk[3], wc, quirk[2]);
+            a2 = cfma(a2, wc, quirk[1]);
+            a2 = cfma(a2, wc, quirk[0]);
+            acc = cadd(acc, a2);
+        }
+        const unsigned long long key = pack_key(cnorm2(acc), (uint32_t)q);
+        best = key > best ? key : best;
+    }
+    return best;
+}
+
 #ifdef __CUDACC__
 template <int SF, int NGROUPS, int NSLOT>
 struct GSmem {
@@ -169,6 +274,7 @@ struct GSmem {
     float4 slots[NGROUPS][NSLOT][GCfg<SF>::SLOT_F4];
     uint64_t bars[NGROUPS][NSLOT];
     unsigned long long keys[NGROUPS][GCfg<SF>::W];
+    float2 quirk[NGROUPS][4];
 };
 
 LB_D void group_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -219,10 +325,34 @@ k1_group_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags)
         group_bar(bar_id, C::T);
         float2 g[C::NR][C::M0];
         g_pass1<SF>(t, slot, g);
-        group_bar(bar_id, C::T);                        // exchange-1 reads done
-        g_store2<SF>(t, slot, g);
-        group_bar(bar_id, C::T);
-        unsigned long long best = g_combine<SF>(t, slot, c);
+        unsigned long long best;
+        if constexpr (C::NR == 4) {
+            group_bar(bar_id, C::T);                    // exchange-1 reads done
+            g_store2<SF>(t, slot, g);
+            group_bar(bar_id, C::T);
+            best = g_combine<SF>(t, slot, c);
+        } else {
+            float2 P[GPair<SF>::NP], Pq;
+            if constexpr (C::NR == 2) {
+                g_pair_sf8<SF>(t, g, c, P, Pq);
+            } else {
+                const int odd = t & 1;
+                float2 keep[C::M0 / 2], recv[C::M0 / 2];
+#pragma unroll
+                for (int j = 0; j < C::M0 / 2; j++) {
+                    const float2 lo = g[0][bitrev<C::M0>(j)], hi = g[0][bitrev<C::M0>(j + C::M0 / 2)];
+                    keep[j] = odd ? hi : lo;
+                    const float2 send = odd ? lo : hi;
+                    recv[j].x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                    recv[j].y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                }
+                g_pair_sf9<SF>(t, keep, recv, c, P, Pq);
+            }
+            group_bar(bar_id, C::T);                    // exchange-1 reads done
+            g_store2p<SF>(t, reinterpret_cast<float2 *>(slot), P, Pq, sm.quirk[grp]);
+            group_bar(bar_id, C::T);
+            best = g_combine_p<SF>(t, reinterpret_cast<const float2 *>(slot), sm.quirk[grp], c);
+        }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
@@ -268,11 +398,36 @@ inline void g_emulate(const K1Args &a, uint32_t *bins, float *mags) {
         for (int t = 0; t < C::T; t++) g_store1<SF>(t, slot, v0[t], v1[t]);
         for (int t = 0; t < C::T; t++) g_pass1<SF>(t, slot, g[t]);
         for (int i = 0; i < C::SLOT_F4; i++) slot[i] = make_float4(NAN, NAN, NAN, NAN);
-        for (int t = 0; t < C::T; t++) g_store2<SF>(t, slot, g[t]);
         unsigned long long best = 0ull;
-        for (int t = 0; t < C::T; t++) {
-            const unsigned long long k = g_combine<SF>(t, slot, c[t]);
-            best = k > best ? k : best;
+        if constexpr (C::NR == 4) {
+            for (int t = 0; t < C::T; t++) g_store2<SF>(t, slot, g[t]);
+            for (int t = 0; t < C::T; t++) {
+                const unsigned long long k = g_combine<SF>(t, slot, c[t]);
+                best = k > best ? k : best;
+            }
+        } else {
+            float2 quirk[4] = {};
+            float2 *slot2 = reinterpret_cast<float2 *>(slot);
+            for (int t = 0; t < C::T; t++) {
+                float2 P[GPair<SF>::NP], Pq;
+                if constexpr (C::NR == 2) {
+                    g_pair_sf8<SF>(t, g[t], c[t], P, Pq);
+                } else {
+                    const int odd = t & 1;
+                    float2 keep[C::M0 / 2], recv[C::M0 / 2];
+                    for (int j = 0; j < C::M0 / 2; j++) {
+                        const int mine = bitrev<C::M0>(j + (odd ? C::M0 / 2 : 0));
+                        keep[j] = g[t][0][mine];
+                        recv[j] = g[t ^ 1][0][mine];          // what the partner sends: its value at MY ka
+                    }
+                    g_pair_sf9<SF>(t, keep, recv, c[t], P, Pq);
+                }
+                g_store2p<SF>(t, slot2, P, Pq, quirk);
+            }
+            for (int t = 0; t < C::T; t++) {
+                const unsigned long long k = g_combine_p<SF>(t, slot2, quirk, c[t]);
+                best = k > best ? k : best;
+            }
         }
         bins[sym] = key_idx(best);
         if (mags) mags[sym] = sqrtf(key_mag2(best));
