@@ -31,9 +31,11 @@ LB_HD void s10_consts(int t, const float2 *tw, S10Consts &c) {
     }
 }
 
+// CHIRP_GLOBAL: the chirp pointer is global memory (read-only path) instead of shared memory
+template <bool CHIRP_GLOBAL = false>
 LB_HD void s10_pass0(int t, const float2 *slot, const float2 *chirp, const S10Consts &c, float2 *v) {
 #pragma unroll
-    for (int r = 0; r < 32; r++) v[r] = cmul(slot[r * S10_T + t], k1_ld_table(chirp + r * S10_T + t));
+    for (int r = 0; r < 32; r++) v[r] = cmul(slot[r * S10_T + t], CHIRP_GLOBAL ? k1_ld_table(chirp + r * S10_T + t) : chirp[r * S10_T + t]);
     dft_dif<32>(v);
 #pragma unroll
     for (int kc = 1; kc < 32; kc++) {
@@ -201,7 +203,7 @@ k1_sf10b_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags)
         float2 *slot = sm.slot;
         mbar_wait(&sm.bar, it & 1u);
         float2 v[32];
-        s10_pass0(t, slot, a.chirp, c, v);
+        s10_pass0<true>(t, slot, a.chirp, c, v);
         __syncthreads();
         s10_store1(t, slot, v);
         __syncthreads();
