@@ -6,6 +6,9 @@
 // sample n = 256 c + t), pass 1 a radix-32 over the 32 columns of output column kc.  The inter-pass
 // twiddle W_N^{a kc} (31 values per lane) is formed from two short lane-invariant tables,
 // W^{a (kc & 3)} and W^{a (kc & ~3)}.
+// Measured alternatives (removed): one slot per CTA with the chirp read through L1 and two CTAs per SM
+// (0.52), and two single-slot groups per CTA sharing the chirp (0.50): both lose to the 2-slot ring (0.58) --
+// the TMA prefetch is worth more than the extra resident warps.
 #pragma once
 #include "k1_group.cuh"
 
@@ -31,11 +34,9 @@ LB_HD void s10_consts(int t, const float2 *tw, S10Consts &c) {
     }
 }
 
-// CHIRP_GLOBAL: the chirp pointer is global memory (read-only path) instead of shared memory
-template <bool CHIRP_GLOBAL = false>
 LB_HD void s10_pass0(int t, const float2 *slot, const float2 *chirp, const S10Consts &c, float2 *v) {
 #pragma unroll
-    for (int r = 0; r < 32; r++) v[r] = cmul(slot[r * S10_T + t], CHIRP_GLOBAL ? k1_ld_table(chirp + r * S10_T + t) : chirp[r * S10_T + t]);
+    for (int r = 0; r < 32; r++) v[r] = cmul(slot[r * S10_T + t], chirp[r * S10_T + t]);
     dft_dif<32>(v);
 #pragma unroll
     for (int kc = 1; kc < 32; kc++) {
@@ -163,68 +164,6 @@ k1_sf10_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags) 
                 fence_proxy_async();
                 mbar_expect_tx(&sm.bars[s], S10_SLOT_BYTES);
                 bulk_g2s(slot, a.x + nxt * S10_SPS, S10_SLOT_BYTES, &sm.bars[s]);
-            }
-            unsigned long long bb = sm.keys[0];
-#pragma unroll
-            for (int k = 1; k < S10_T / 32; k++) bb = sm.keys[k] > bb ? sm.keys[k] : bb;
-            bins[sym] = key_idx(bb);
-            if (mags) mags[sym] = sqrtf(key_mag2(bb));
-        }
-    }
-}
-// Variant B: ONE slot per CTA, chirp read through the read-only path (64 KiB: stays in the L1 that the
-// smaller shared-memory footprint leaves), 128 registers -> two CTAs per SM that run out of phase, so
-// one loads / waits at its barriers while the other computes.
-struct S10SmemB {
-    float2 slot[S10_SLOT_F2];
-    uint64_t bar;
-    unsigned long long keys[S10_T / 32];
-};
-
-__global__ void __launch_bounds__(S10_T, 2)
-k1_sf10b_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags) {
-    extern __shared__ __align__(128) unsigned char s10b_raw[];
-    S10SmemB &sm = *reinterpret_cast<S10SmemB *>(s10b_raw);
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const size_t g0 = blockIdx.x, g_total = gridDim.x;
-    if (t == 0) {
-        mbar_init(&sm.bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (t == 0 && g0 < a.n_symbols) {
-        mbar_expect_tx(&sm.bar, S10_SLOT_BYTES);
-        bulk_g2s(sm.slot, a.x + g0 * S10_SPS, S10_SLOT_BYTES, &sm.bar);
-    }
-    S10Consts c;
-    s10_consts(t, a.tw, c);
-    uint32_t it = 0;
-    for (size_t sym = g0; sym < a.n_symbols; sym += g_total, it++) {
-        float2 *slot = sm.slot;
-        mbar_wait(&sm.bar, it & 1u);
-        float2 v[32];
-        s10_pass0<true>(t, slot, a.chirp, c, v);
-        __syncthreads();
-        s10_store1(t, slot, v);
-        __syncthreads();
-        s10_pass1(t, slot, v);
-        __syncthreads();
-        s10_store2(t, slot, v);
-        __syncthreads();
-        unsigned long long best = s10_combine(t, slot, c);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o > best ? o : best;
-        }
-        if (lane == 0) sm.keys[warp] = best;
-        __syncthreads();
-        if (t == 0) {
-            const size_t nxt = sym + g_total;
-            if (nxt < a.n_symbols) {
-                fence_proxy_async();
-                mbar_expect_tx(&sm.bar, S10_SLOT_BYTES);
-                bulk_g2s(slot, a.x + nxt * S10_SPS, S10_SLOT_BYTES, &sm.bar);
             }
             unsigned long long bb = sm.keys[0];
 #pragma unroll

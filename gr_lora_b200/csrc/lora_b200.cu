@@ -269,23 +269,7 @@ int launch_k1_cluster(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, 
 }
 
 // SF10: one 256-thread group per symbol, two radix-32 passes (k1_sf10.cuh)
-int launch_k1_sf10b(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
-    static bool attr_set[64] = {};
-    const size_t smem = sizeof(S10SmemB);
-    if (!attr_set[d->device & 63]) {
-        CU(cudaFuncSetAttribute(k1_sf10b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[d->device & 63] = true;
-    }
-    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    const int grid = (int)std::min<size_t>(n_symbols, (size_t)d->n_sms * 2);
-    k1_sf10b_kernel<<<grid, S10_T, smem, st>>>(a, bins, mags);
-    d->launches++;
-    CU(cudaGetLastError());
-    return LORA_B200_OK;
-}
-
 int launch_k1_sf10(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
-    if (getenv("LORA_B200_K1_SF10B")) return launch_k1_sf10b(d, iq, n_symbols, bins, mags, st);
     static bool attr_set[64] = {};
     const size_t smem = sizeof(S10Smem<2>);
     if (!attr_set[d->device & 63]) {
