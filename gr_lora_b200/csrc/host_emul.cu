@@ -7,6 +7,7 @@
 #include "k1_cluster.cuh"
 #include "k1_sf10.cuh"
 #include "k1_big.cuh"
+#include "k1_xchg.cuh"
 #include "int_chain.cuh"
 
 extern "C" {
@@ -50,6 +51,20 @@ int lb_k1_emulate_big(int sf, const float2 *x, size_t n_symbols, const float2 *c
     lb::K1Args a{x, chirp, tw, n_symbols};
     if (sf == 11) lb::b_emulate<11>(a, bins, mags);
     else if (sf == 12) lb::b_emulate<12>(a, bins, mags);
+    else return -1;
+    return 0;
+}
+
+int lb_k1_emulate_xchg(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
+    lb::K1Args a{x, chirp, tw, n_symbols};
+    const int th = sf / 100 ? 128 : 256;                 // sf + 100 selects the 128-thread variant
+    sf %= 100;
+    if (sf == 10 && th == 256) lb::xg_emulate<10, 256>(a, bins, mags);
+    else if (sf == 11 && th == 256) lb::xg_emulate<11, 256>(a, bins, mags);
+    else if (sf == 12 && th == 256) lb::xg_emulate<12, 256>(a, bins, mags);
+    else if (sf == 10) lb::xg_emulate<10, 128>(a, bins, mags);
+    else if (sf == 11) lb::xg_emulate<11, 128>(a, bins, mags);
+    else if (sf == 12) lb::xg_emulate<12, 128>(a, bins, mags);
     else return -1;
     return 0;
 }

@@ -9,6 +9,7 @@
 #include "k1_cluster.cuh"
 #include "k1_sf10.cuh"
 #include "k1_big.cuh"
+#include "k1_xchg.cuh"
 #include "rx_stream.cuh"
 
 #include <algorithm>
@@ -62,6 +63,8 @@ struct lora_b200_decoder {
     // K1
     unsigned long long *d_packed = nullptr;
     size_t packed_cap = 0;
+    void *d_xs = nullptr;                 // k1_xchg: exchange scratch + flags
+    size_t xs_cap = 0;
     float *d_k2_scratch = nullptr;
     int k2_grid = 0;
     // e2e host path
@@ -323,6 +326,68 @@ int launch_k1_big(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint
     return LORA_B200_OK;
 }
 
+// k1_xchg watchdog: with LORA_B200_XG_WATCHDOG set, spins that last too long leave a record in host-mapped memory that
+// lora_b200_xg_watchdog() exposes (tools/k1_ab.py reads it while a kernel hangs).  Not part of the public header.
+static unsigned long long *g_xg_wd_host = nullptr, *g_xg_wd_dev = nullptr;
+unsigned long long *xg_watchdog_dev() {
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        if (getenv("LORA_B200_XG_WATCHDOG") && cudaHostAlloc(&g_xg_wd_host, 256 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+            memset(g_xg_wd_host, 0, 256 * sizeof(unsigned long long));
+            if (cudaHostGetDevicePointer(&g_xg_wd_dev, g_xg_wd_host, 0) != cudaSuccess) g_xg_wd_dev = nullptr;
+        }
+    }
+    return g_xg_wd_dev;
+}
+
+// SF10/SF11/SF12: teams of CL sub-CTAs per symbol, pass-0 outputs exchanged through an L2-resident scratch with TMA
+// stores / loads and global flags; one 512-thread CTA (512 / TH sub-CTAs) per SM (k1_xchg.cuh)
+template <int SF, int TH>
+int launch_k1_xchg(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    using X = XCfg<SF, TH>;
+    constexpr int NH = 512 / TH;
+    static int max_cta_teams[64] = {};
+    const size_t smem = sizeof(XSmem<TH>);
+    if (!max_cta_teams[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_xchg_kernel<SF, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_xchg_kernel<SF, TH>, 512, smem));
+        int nt = (per_sm > 0 ? 1 : 0) * d->n_sms / X::CL;     // every CTA of the grid must be resident (teams spin on flags)
+        if (nt < 1) return fail(LORA_B200_ECUDA, "k1_xchg: a team of %d CTAs does not fit on the device", X::CL);
+        static const char *cap = getenv("LORA_B200_K1_XCHG_TEAMS");        // tuning knob
+        if (cap && atoi(cap) > 0 && atoi(cap) < nt) nt = atoi(cap);
+        max_cta_teams[d->device & 63] = nt;
+    }
+    // a CTA-team = CL CTAs = NH teams; do not launch CTA-teams that would get no symbol
+    const size_t n_ct = std::max<size_t>(1, std::min<size_t>((n_symbols + NH - 1) / NH, (size_t)max_cta_teams[d->device & 63]));
+    const size_t n_teams = n_ct * NH;
+    if (d->packed_cap < n_symbols) {
+        if (d->d_packed) cudaFree(d->d_packed);
+        d->d_packed = nullptr; d->packed_cap = 0;
+        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
+        d->packed_cap = n_symbols;
+    }
+    const size_t xs_bytes = n_teams * XG_NB * ((size_t)X::SPS * sizeof(float2) + sizeof(uint32_t));
+    if (d->xs_cap < xs_bytes) {
+        if (d->d_xs) cudaFree(d->d_xs);
+        d->d_xs = nullptr; d->xs_cap = 0;
+        CU(cudaMalloc(&d->d_xs, xs_bytes));
+        d->xs_cap = xs_bytes;
+    }
+    float2 *xs = reinterpret_cast<float2 *>(d->d_xs);
+    uint32_t *flags = reinterpret_cast<uint32_t *>(xs + n_teams * XG_NB * (size_t)X::SPS);
+    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    CU(cudaMemsetAsync(flags, 0, n_teams * XG_NB * sizeof(uint32_t), st));
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    k1_xchg_kernel<SF, TH><<<(unsigned)(n_ct * X::CL), 512, smem, st>>>(a, xs, flags, d->d_packed, xg_watchdog_dev(), getenv("LORA_B200_XG_NOSYNC") ? 1 : 0);
+    d->launches++;
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
     static int v = -1;
     if (v < 0) {
@@ -369,6 +434,18 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
             if (gv && gv[0] == 'b') return launch_k1_group<9, 2, 2>(d, iq, n, bins, mags, st);
             return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
         }
+        static const char *xg = getenv("LORA_B200_K1_XCHG");          // digits = SFs that use k1_xchg ("012" = SF10,11,12)
+        if (xg && d->cfg.sf >= 10 && strchr(xg, '0' + (d->cfg.sf - 10))) {
+            static const char *xt = getenv("LORA_B200_K1_XCHG_T");    // "128": 128-thread CTAs, clusters of 4/8/16
+            if (xt && atoi(xt) == 128) {
+                if (d->cfg.sf == 10) return launch_k1_xchg<10, 128>(d, iq, n, bins, mags, st);
+                if (d->cfg.sf == 11) return launch_k1_xchg<11, 128>(d, iq, n, bins, mags, st);
+                return launch_k1_xchg<12, 128>(d, iq, n, bins, mags, st);
+            }
+            if (d->cfg.sf == 10) return launch_k1_xchg<10, 256>(d, iq, n, bins, mags, st);
+            if (d->cfg.sf == 11) return launch_k1_xchg<11, 256>(d, iq, n, bins, mags, st);
+            return launch_k1_xchg<12, 256>(d, iq, n, bins, mags, st);
+        }
         if (d->cfg.sf == 10 && !getenv("LORA_B200_K1_SF10_GENERIC")) return launch_k1_sf10(d, iq, n, bins, mags, st);
         // k1_big (cluster of TMA-fed groups) measured 0.287 (SF11) / 0.130 (SF12): membar + lg_throttle stalls
         // around the two cluster barriers (profiles/r1_k1_big_sf11.md); the simpler kernels below are faster
@@ -378,8 +455,10 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
             if (d->cfg.sf == 12) return launch_k1_big<12>(d, iq, n, bins, mags, st);
         }
         if (d->cfg.sf == 11) return launch_k1_cluster<11>(d, iq, n, bins, mags, st);
-        // SF12: the 4-CTA cluster version measured slower (0.107) than the DIF-split version (0.129): keep the latter
+        // SF12: the 4-CTA cluster version measured slower (0.107) than the DIF-split version (0.146); the team kernel
+        // (k1_xchg.cuh, exchange through L2) measures 0.23 and is the default
         if (d->cfg.sf == 12 && getenv("LORA_B200_K1_SF12_CLUSTER")) return launch_k1_cluster<12>(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 12 && !getenv("LORA_B200_K1_SF12_GENERIC")) return launch_k1_xchg<12, 256>(d, iq, n, bins, mags, st);
     }
     switch (d->cfg.sf) {
     case 7: return launch_k1<7>(d, iq, n, bins, mags, st);
@@ -498,6 +577,9 @@ int run_rx(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t
 // =================================================================================================
 // C ABI
 // =================================================================================================
+// internal (tools/k1_ab.py): host view of the k1_xchg watchdog records, NULL unless LORA_B200_XG_WATCHDOG is set
+extern "C" const unsigned long long *lora_b200_xg_watchdog() { return g_xg_wd_host; }
+
 extern "C" {
 
 const char *lora_b200_last_error(void) { return g_err.c_str(); }
@@ -599,7 +681,7 @@ void lora_b200_destroy(lora_b200_decoder *d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
-    cudaFree(d->d_tables); cudaFree(d->d_packed); cudaFree(d->d_k2_scratch);
+    cudaFree(d->d_tables); cudaFree(d->d_packed); cudaFree(d->d_xs); cudaFree(d->d_k2_scratch);
     for (int i = 0; i < 2; i++) {
         if (d->copy_streams[i]) cudaStreamDestroy(d->copy_streams[i]);
         cudaFree(d->d_chunk[i]); cudaFree(d->d_chunk_bins[i]); cudaFree(d->d_chunk_mags[i]);
