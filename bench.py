@@ -191,6 +191,16 @@ def synth_batch(torch, sf, channels, n_sym, snr_db, device, seed):
     return iq, vals
 
 
+def workload_name(args, sf):
+    """One string for both arms (the driver compares metric + config of the two JSON lines)."""
+    return (f"batched synthetic SF{sf} BW125k, 1 MS/s IQ, {args.channels} concurrent channels x "
+            f"{args.symbols_per_channel} symbols per GPU (BASELINE.json configs[1])")
+
+
+K1_KERNEL = {7: "k1_sf7_warp_kernel<12,2>", 8: "k1_group_kernel<8,6,2>", 9: "k1_group_kernel<9,3,2>", 10: "k1_sf10_kernel<2>",
+             11: "k1_cluster_kernel<11>", 12: "k1_xchg_kernel<12,256>"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU get_shift_fft path (oracle port) on all host threads."""
     rank = int(os.environ.get("RANK", "0"))
@@ -210,8 +220,9 @@ def run_reference(args):
         "impl": "reference", "metric": "LoRa symbols/s (dechirp+FFT+argmax)", "value": value, "unit": "symbols/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"batched synthetic SF{args.sf} BW125k 1 MS/s, {args.channels} channels x "
-                               f"{args.symbols_per_channel} symbols", "sf": args.sf},
+        "config": {"workload": workload_name(args, args.sf), "sf": args.sf, "channels_per_gpu": args.channels,
+                   "symbols_per_channel": args.symbols_per_channel, "snr_db": args.snr_db,
+                   "parallelism": f"host threads x{threads} (rank 0 only)"},
         "cpu_baseline": {"value": value, "unit": "symbols/s", "cores": threads, "kind": "port",
                          "sample": f"{per_step:.1f} s of get_shift_fft per step on {threads} threads "
                                    f"({total_syms} symbols timed), CPU {cpu_model()}; the reference cannot be built "
@@ -390,15 +401,14 @@ def main():
             "metric": "LoRa symbols/s (dechirp+FFT+argmax)", "value": value, "unit": "symbols/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"batched synthetic SF{sf} BW125k, 1 MS/s IQ, {args.channels} concurrent channels x "
-                                   f"{args.symbols_per_channel} symbols per GPU (BASELINE.json configs[1])",
+            "config": {"workload": workload_name(args, sf),
                        "sf": sf, "channels_per_gpu": args.channels, "symbols_per_channel": args.symbols_per_channel,
                        "snr_db": args.snr_db, "batch_bytes_per_gpu": int(n_sym_total * sps * 8),
                        "l2": "inputs (8 GiB) larger than L2, no flush needed", "parallelism": f"streams sharded x{world}",
                        "demod_accuracy_vs_tx": acc},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "k1_sf7_warp_kernel<12,2>" if sf == 7 and os.environ.get("LORA_B200_K1", "w12x2") == "w12x2" else f"k1_fft_kernel<{sf}>",
+                         "kernel": K1_KERNEL.get(sf, "?") if os.environ.get("LORA_B200_K1", "w12x2") == "w12x2" else f"k1_fft_kernel<{sf}>",
                          "algorithmic_bytes_per_launch": int(abytes)},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "cpu_baseline": cpu,
         }
