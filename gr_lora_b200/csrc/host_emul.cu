@@ -8,6 +8,7 @@
 #include "k1_sf10.cuh"
 #include "k1_big.cuh"
 #include "k1_xchg.cuh"
+#include "k1_ab.cuh"
 #include "int_chain.cuh"
 
 extern "C" {
@@ -65,6 +66,15 @@ int lb_k1_emulate_xchg(int sf, const float2 *x, size_t n_symbols, const float2 *
     else if (sf == 10) lb::xg_emulate<10, 128>(a, bins, mags);
     else if (sf == 11) lb::xg_emulate<11, 128>(a, bins, mags);
     else if (sf == 12) lb::xg_emulate<12, 128>(a, bins, mags);
+    else return -1;
+    return 0;
+}
+
+int lb_k1_emulate_ab(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
+    lb::K1Args a{x, chirp, tw, n_symbols};
+    if (sf == 10) lb::ab_emulate<10>(a, bins, mags);
+    else if (sf == 11) lb::ab_emulate<11>(a, bins, mags);
+    else if (sf == 12) lb::ab_emulate<12>(a, bins, mags);
     else return -1;
     return 0;
 }

@@ -10,6 +10,7 @@
 #include "k1_sf10.cuh"
 #include "k1_big.cuh"
 #include "k1_xchg.cuh"
+#include "k1_ab.cuh"
 #include "rx_stream.cuh"
 
 #include <algorithm>
@@ -388,6 +389,52 @@ int launch_k1_xchg(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uin
     return LORA_B200_OK;
 }
 
+// SF10/SF11/SF12: producer / consumer roles in one persistent kernel, exchange in L2 (k1_ab.cuh)
+template <int SF>
+int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    using A = ACfg<SF>;
+    static int n_a_ctas[64] = {};
+    const size_t smem = sizeof(ABSmem);
+    if (!n_a_ctas[d->device & 63]) {
+        CU(cudaFuncSetAttribute(k1_ab_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_ab_kernel<SF>, AB_WARPS * 32, smem));
+        if (per_sm < 1) return fail(LORA_B200_ECUDA, "k1_ab: the kernel does not fit on an SM");
+        int na = 48;                                      // role A CTAs; 12 warps each, their total a multiple of 32
+        static const char *e = getenv("LORA_B200_K1_AB_NA");
+        if (e && atoi(e) >= 8) na = atoi(e) / 8 * 8;
+        if (na > d->n_sms - 8) na = (d->n_sms - 8) / 8 * 8;
+        if (na < 8) return fail(LORA_B200_ECUDA, "k1_ab: needs at least 16 SMs");
+        n_a_ctas[d->device & 63] = na;
+    }
+    const uint32_t na = (uint32_t)n_a_ctas[d->device & 63], nb = (uint32_t)d->n_sms - na;   // one CTA per SM: all resident
+    const uint32_t ring = (uint32_t)((32u << 20) / ((size_t)A::SPS * sizeof(float2)));      // 32 MiB of exchange buffers
+    if (d->packed_cap < n_symbols) {
+        if (d->d_packed) cudaFree(d->d_packed);
+        d->d_packed = nullptr; d->packed_cap = 0;
+        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
+        d->packed_cap = n_symbols;
+    }
+    const size_t xs_bytes = (size_t)ring * A::SPS * sizeof(float2) + 2 * ring * sizeof(uint32_t);
+    if (d->xs_cap < xs_bytes) {
+        if (d->d_xs) cudaFree(d->d_xs);
+        d->d_xs = nullptr; d->xs_cap = 0;
+        CU(cudaMalloc(&d->d_xs, xs_bytes));
+        d->xs_cap = xs_bytes;
+    }
+    float2 *scratch = reinterpret_cast<float2 *>(d->d_xs);
+    uint32_t *ready = reinterpret_cast<uint32_t *>(scratch + (size_t)ring * A::SPS), *done = ready + ring;
+    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    CU(cudaMemsetAsync(ready, 0, 2 * ring * sizeof(uint32_t), st));
+    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
+    k1_ab_kernel<SF><<<na + nb, AB_WARPS * 32, smem, st>>>(a, scratch, ready, done, ring, nb, d->d_packed, xg_watchdog_dev());
+    d->launches++;
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
     static int v = -1;
     if (v < 0) {
@@ -433,6 +480,12 @@ int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins
             if (gv && gv[0] == 'a') return launch_k1_group<9, 2, 3>(d, iq, n, bins, mags, st);
             if (gv && gv[0] == 'b') return launch_k1_group<9, 2, 2>(d, iq, n, bins, mags, st);
             return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
+        }
+        static const char *ab = getenv("LORA_B200_K1_AB");            // digits = SFs that use k1_ab ("012" = SF10,11,12)
+        if (ab && d->cfg.sf >= 10 && strchr(ab, '0' + (d->cfg.sf - 10))) {
+            if (d->cfg.sf == 10) return launch_k1_ab<10>(d, iq, n, bins, mags, st);
+            if (d->cfg.sf == 11) return launch_k1_ab<11>(d, iq, n, bins, mags, st);
+            return launch_k1_ab<12>(d, iq, n, bins, mags, st);
         }
         static const char *xg = getenv("LORA_B200_K1_XCHG");          // digits = SFs that use k1_xchg ("012" = SF10,11,12)
         if (xg && d->cfg.sf >= 10 && strchr(xg, '0' + (d->cfg.sf - 10))) {

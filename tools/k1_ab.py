@@ -16,7 +16,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-SITES = {1: "A: slot_full", 2: "A: gate rx_full", 3: "B: rx_full", 4: "fetch: flag poll", 5: "B: slot_free"}
+SITES = {1: "A: slot_full", 2: "A: gate rx_full", 3: "B: rx_full", 4: "fetch: flag poll", 5: "B: slot_free", 6: "ab A: done[slot]", 7: "ab B: ready[slot]", 8: "ab B: TMA row", 9: "ab A: TMA rows"}
 
 
 def guard(torch, seconds, what):
