@@ -174,7 +174,8 @@ k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ read
         ab_consts<SF>(col, a.tw, c);
         for (int s = 0; s < AB_NSLOT; s++)
             if ((size_t)s < n_items) a_issue(s, s);
-        constexpr int PUB = 4;                            // publish every PUB items: one gpu-scope fence per PUB * U symbols
+        constexpr int PUB = 1;                            // publish every PUB items (one gpu-scope fence each); what is stored but
+                                                          // unpublished counts against the ring (see launch_k1_ab)
         uint32_t pend[PUB * U];                           // ring slots stored but not yet published
         int n_pend = 0;
         for (size_t item = 0; item < n_items; item++) {

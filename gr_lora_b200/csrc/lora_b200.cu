@@ -408,7 +408,12 @@ int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint3
         n_a_ctas[d->device & 63] = na;
     }
     const uint32_t na = (uint32_t)n_a_ctas[d->device & 63], nb = (uint32_t)d->n_sms - na;   // one CTA per SM: all resident
-    const uint32_t ring = (uint32_t)((32u << 20) / ((size_t)A::SPS * sizeof(float2)));      // 32 MiB of exchange buffers
+    // exchange ring: role B looks 3 items per warp ahead (2 in its TMA ring + 1 in work) = 3 * 12 * nb / R symbols, role A
+    // has 2 * 12 * na / 32 * (32 / R) symbols in work or unpublished: together ~36 MiB at every SF; 48 MiB leave slack
+    // and still sit in the 126 MB L2 beside the streaming input
+    static const char *rmb = getenv("LORA_B200_K1_AB_RING_MB");
+    const size_t ring_mb = rmb && atoi(rmb) >= 8 ? (size_t)atoi(rmb) : 48;
+    const uint32_t ring = (uint32_t)((ring_mb << 20) / ((size_t)A::SPS * sizeof(float2)));
     if (d->packed_cap < n_symbols) {
         if (d->d_packed) cudaFree(d->d_packed);
         d->d_packed = nullptr; d->packed_cap = 0;
