@@ -1,19 +1,16 @@
-// k1_xchg.cuh -- K1 for SF10 / SF11 / SF12: a cluster of CL = 2 / 4 / 8 CTAs per symbol with an ASYNCHRONOUS
-// all-to-all over distributed shared memory (bulk smem->peer-smem copies completing on the receiver's
-// mbarrier), two CTAs resident per SM.
+// k1_xchg.cuh -- K1 for SF10 / SF11 / SF12: a TEAM of CL sub-CTAs (on CL different SMs) per symbol, the symbol split by
+// columns, the all-to-all between pass 0 and the rest through an L2-resident scratch in global memory.  Default for SF12.
 //
-// Why (profiles/r1_k1_big_sf11.md): the first cluster kernel (k1_big.cuh) read every sample once and was lean
-// in instructions (47 per sample) but used 30 % of the issue slots: one 256-thread group per SM in lock step,
-// two cluster-wide barriers per symbol (membar / wait stalls) and 8-byte remote stores (lg_throttle).  Here
-//   * a CTA owns 32 KiB of the symbol (16 rows x 256 columns), a thread 16 values (radix 16, <= 128
-//     registers), so TWO CTAs of different clusters share an SM and fill each other's waits;
-//   * pass-0 results go back IN PLACE into the consumed TMA slot as 16 runs of 2 KiB (one per output column
-//     kc) and the copy engine moves run kc into the receive buffer of CTA kc / KPC
-//     (cp.async.bulk.shared::cluster.shared::cta ... mbarrier::complete_tx at the receiver): no remote LSU
-//     stores, no cluster barrier;  flow control is one credit mbarrier per CTA (every peer arrives on it when
-//     it has finished with its receive buffer);
-//   * the TMA slot is refilled as soon as the outgoing copies have read it, i.e. the next symbol streams in
-//     during pass 1, pass 2 and the combine.
+// History of this file (profiles/r1_k1_xchg_sf12.md has the table).  The first cluster kernel (k1_big.cuh) read every
+// sample once and was lean in instructions but used 30 % of the issue slots: one 256-thread group per SM in lock step,
+// two cluster-wide barriers per symbol, 8-byte remote stores.  The versions tried here, same arithmetic every time:
+//   1. hardware clusters, pass-0 outputs moved by cp.async.bulk smem -> peer smem with mbarrier complete_tx at the
+//      receiver and credit mbarriers: no cluster barrier, but the copy engine moves only ~10 GB/s per SM;
+//   2. no hardware cluster: TMA stores into an L2-resident scratch, flags in global memory, TMA loads back;
+//   3. one 512-thread CTA per SM = two sub-CTAs sharing the chirp columns, pass 0 two symbols ahead, outputs stored
+//      straight from registers, double-buffered TMA slots (the consumed one is the step's scratch), group barriers
+//      only, control by the last warp to arrive  <- what is below.
+// All of them land at 0.21-0.28 of the HBM peak; switching the cross-SM waits off changes < 10 %.
 //
 // Index algebra (get_shift_fft, lib/decoder_impl.cc:430-464; pruned DFT as in k1_fft.cuh).  sample n = 8 n1 + r,
 // n1 = c L + a (row c < 16, a < L = N/16), kept bin k = kc + 16 ka (kc < 16, ka < L):
@@ -36,7 +33,7 @@ struct XCfg {
     static constexpr int N = 1 << SF, SPS = 8 * N;
     static constexpr int L = N / 16;                     // length of the per-kc FFT
     static constexpr int ROWLEN = 8 * L;                 // samples per row; 16 rows per symbol
-    static constexpr int CL = ROWLEN / TH;               // CTAs per cluster: TH=256: 2, 4, 8;  TH=128: 4, 8, 16
+    static constexpr int CL = ROWLEN / TH;               // sub-CTAs per team: TH=256: 2, 4, 8;  TH=128: 4, 8, 16
     static constexpr int AW = TH / 8;                    // columns a per CTA
     static constexpr int M2 = L / 16;                    // 4, 8, 16
     static constexpr int KPC = 16 / CL;                  // output columns kc per CTA
@@ -225,14 +222,7 @@ LB_HD unsigned long long xg_combine(int t, int rank, const float2 *s2, const XCo
 }
 
 #ifdef __CUDACC__
-// ---- TMA store / flag primitives --------------------------------------------------------------------------
-LB_D void xg_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-                 ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-LB_D void xg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-LB_D void xg_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-LB_D void xg_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// ---- flag primitives --------------------------------------------------------------------------
 LB_D void xg_fence_proxy_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 LB_D void xg_flag_add(uint32_t *flag) { asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory"); }
 LB_D uint32_t xg_flag_ld(const uint32_t *flag) {
@@ -447,7 +437,7 @@ k1_xchg_kernel(K1Args a, float2 *__restrict__ xs, uint32_t *__restrict__ flags, 
 }
 #endif
 
-// CPU emulation: the CL CTAs of a cluster run one after another, phase by phase
+// CPU emulation: the CL sub-CTAs of a team run one after another, phase by phase
 template <int SF, int TH>
 inline void xg_emulate(const K1Args &a, uint32_t *bins, float *mags) {
     using X = XCfg<SF, TH>;
