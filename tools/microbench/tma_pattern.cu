@@ -82,6 +82,10 @@ int main() {
         {" 8 x 4 KiB, stride 32 KiB", 32768, 8, 32768, 2},
         {" 4 x 8 KiB, stride 64 KiB", 32768, 4, 65536, 2},
         {"32 x 2 KiB, stride  8 KiB (k1_big SF11)", 65536, 32, 8192, 1},
+        {"32 x 256 B, stride  8 KiB (k1_ab role A), 12 warps/SM", 8192, 32, 8192, 12},
+        {"32 x 256 B, stride  8 KiB (k1_ab role A),  8 warps/SM", 8192, 32, 8192, 8},
+        {"32 x 512 B, stride  8 KiB, 6 warps/SM", 16384, 32, 8192, 6},
+        {"32 x 1 KiB, stride  8 KiB, 3 warps/SM", 32768, 32, 8192, 3},
     };
     constexpr int NSLOT = 3;
     for (const Case &c : cases) {
