@@ -15,6 +15,7 @@ import sys
 import numpy as np
 
 from . import _native as N
+from .loraphy import parse_frame
 
 LORATAP_LEN = 15   # sizeof(loratap_header_t), include/lora/loratap.h:48-55
 LORAPHY_LEN = 3    # sizeof(loraphy_header_t), include/lora/loraphy.h:25-32
@@ -64,6 +65,9 @@ class decoder:
         self.decim = self._L.lora_b200_decimation(h)
         self.quiet = quiet
         self.frames = []            # what was published on message port "frames": (stream, bytes)
+        self.implicit = bool(implicit)
+        self.header_checks = {"ok": 0, "bad": 0}   # explicit-header checksum of the published frames (loraphy.py; the
+                                                   # reference never checks it, include/lora/utilities.h:396-404)
         self._handlers = []
         self._cb = N.FRAME_CB(self._on_frame)
         buf = C.create_string_buffer(512)
@@ -105,6 +109,8 @@ class decoder:
     def _on_frame(self, _user, stream, data, length):
         blob = bytes(C.string_at(data, length))
         self.frames.append((int(stream), blob))
+        if not self.implicit and len(blob) >= 18:     # side channel only: the published bytes are never touched
+            self.header_checks["ok" if parse_frame(blob).header_ok else "bad"] += 1
         for h in self._handlers:
             h(int(stream), blob)
 
