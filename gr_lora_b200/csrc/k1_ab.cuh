@@ -132,17 +132,142 @@ LB_D void ab_spin(const uint32_t *flag, uint32_t need, unsigned long long *dbg, 
         if (++spins == (1u << 18)) xg_dbg(dbg, site, 0, warp, sym, got);
 }
 
+LB_D void ab_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+LB_D void ab_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+LB_D void ab_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+LB_D void ab_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Role A, version 2 (prod == 2): a GROUP of 4 warps owns 128 columns.  An item = 32 row pieces of 1 KiB (U symbols x R
+// rows) in one 32 KiB slot of the group's 2-slot TMA ring; thread t of the group owns column t: it reads its 32 values,
+// dechirps, runs the radix-R row pass and writes the outputs back IN PLACE (it overwrites only what it read), then one
+// thread hands the 32 rows to the copy engine (32 bulk stores of 1 KiB into the exchange ring) and refills the slot as
+// soon as those stores have read it.  The ready flags of an item are raised one item later, after
+// cp.async.bulk.wait_group has confirmed its stores: no gpu-scope fence and no scattered LSU stores on the critical
+// path, one named barrier per item.  (Version 1's warp spent 20 % of its time issuing 32 x 256 B copies lane by lane,
+// 27 % on polls and 256 B stores, 13 % in fences, 8 % on arithmetic: profiles/r1_k1_ab_sf12.md.)
+template <int SF>
+LB_D void ab_producer_groups(const K1Args &a, float2 *scratch, uint32_t *ready, const uint32_t *done, uint32_t ring, uint32_t n_b,
+                             unsigned char *smem_raw, unsigned long long *dbg) {
+    using A = ACfg<SF>;
+    constexpr int U = 32 / A::R, GT = 128, TILES = A::COLS / GT;           // 8 column tiles per symbol
+    constexpr uint32_t SLOT_BYTES = 32u * GT * 8u;                          // 32 KiB
+    const int grp = threadIdx.x / GT, t = threadIdx.x % GT, lane = threadIdx.x & 31;
+    float2 *slots = reinterpret_cast<float2 *>(smem_raw + sizeof(float4) * W7_SLOT_F4) + (size_t)grp * 2 * (SLOT_BYTES / 8);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + sizeof(float4) * W7_SLOT_F4 + (size_t)AB_WARPS * AB_NSLOT * W7_SLOT_F4 * sizeof(float4))
+                     + grp * 8;                           // the mbarrier words of the group's first warp
+    const size_t n_ag = (size_t)(gridDim.x - n_b) * 3;    // groups; a multiple of TILES (host side)
+    const size_t g = (size_t)(blockIdx.x - n_b) * 3 + grp;
+    const int colbase = (int)(g % TILES) * GT, col = colbase + t;
+    const size_t step = n_ag / TILES, first = g / TILES;  // this group's symbols: first, first + step, ...
+    const size_t n_mine = first < a.n_symbols ? (a.n_symbols - first + step - 1) / step : 0;
+    const size_t n_items = (n_mine + U - 1) / U;
+    auto group_sync = [&]() {
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else if (grp == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 3, 128;" ::: "memory");
+    };
+    if (t == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    group_sync();
+    auto sym_of = [&](size_t item, int u) { return first + (item * U + u) * step; };
+    auto issue_loads = [&](size_t item, int si) {        // one thread: 32 row pieces of 1 KiB
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++) if (sym_of(item, u) < a.n_symbols) bytes += A::R * 1024u;
+        mbar_expect_tx(&bars[si], bytes);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t s = sym_of(item, u);
+            if (s >= a.n_symbols) break;
+#pragma unroll
+            for (int r = 0; r < A::R; r++)
+                bulk_g2s(slots + (size_t)si * (SLOT_BYTES / 8) + (u * A::R + r) * GT, a.x + s * (size_t)A::SPS + r * A::COLS + colbase, 1024u, &bars[si]);
+        }
+    };
+    AConsts<SF> c;
+    ab_consts<SF>(col, a.tw, c);
+    if (t == 0)
+        for (int si = 0; si < 2; si++) if ((size_t)si < n_items) issue_loads(si, si);
+    bool stores_pending = false;                          // thread 0: the previous item's stores are not yet published
+    size_t pend_item = 0;
+    for (size_t item = 0; item < n_items; item++) {
+        const int si = (int)(item & 1);
+        float2 *slot = slots + (size_t)si * (SLOT_BYTES / 8);
+        float2 v[U][A::R];
+#pragma unroll
+        for (int r = 0; r < A::R; r++) v[0][r] = k1_ld_table(a.chirp + col + r * A::COLS);      // L2 hits, before the wait
+        xg_wait(&bars[si], (uint32_t)(item >> 1) & 1u, dbg, 9, 0, (unsigned)(threadIdx.x >> 5), (unsigned)item);
+#pragma unroll
+        for (int u = U - 1; u >= 0; u--)
+#pragma unroll
+            for (int r = 0; r < A::R; r++) v[u][r] = cmul(slot[(u * A::R + r) * GT + t], v[0][r]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            ab_column_fft<SF>(c, v[u]);
+#pragma unroll
+            for (int kc = 0; kc < A::R; kc++) slot[(u * A::R + kc) * GT + t] = v[u][bitrev<A::R>(kc)];   // in place
+        }
+        fence_proxy_async();                              // my generic writes -> read by the copy engine
+        group_sync();
+        if (t == 0) {
+            if (stores_pending) {                         // publish the previous item: its stores have had a whole item
+                ab_bulk_wait_all();
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const size_t s = sym_of(pend_item, u);
+                    if (s < a.n_symbols) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ready + (uint32_t)(s % ring)), "r"(GT / 32) : "memory");
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const size_t s = sym_of(item, u);
+                if (s >= a.n_symbols) break;
+                const uint32_t rs = (uint32_t)(s % ring);
+                ab_spin(done + rs, (uint32_t)(A::R * (s / ring)), dbg, 6, (unsigned)(threadIdx.x >> 5), (unsigned)s);
+#pragma unroll
+                for (int kc = 0; kc < A::R; kc++)
+                    ab_bulk_s2g(scratch + ((size_t)rs * A::R + kc) * A::COLS + colbase, slot + (u * A::R + kc) * GT, 1024u);
+            }
+            ab_bulk_commit();
+            stores_pending = true;
+            pend_item = item;
+            if (item + 2 < n_items) {                     // refill the slot once the stores have read it
+                ab_bulk_wait_read();
+                issue_loads(item + 2, si);
+            }
+        }
+    }
+    if (t == 0 && stores_pending) {
+        ab_bulk_wait_all();
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t s = sym_of(pend_item, u);
+            if (s < a.n_symbols) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ready + (uint32_t)(s % ring)), "r"(GT / 32) : "memory");
+        }
+    }
+    (void)lane;
+}
+
 // scratch: [ring][R][1024] float2; ready / done: [ring] counters (zeroed before the launch)
 template <int SF>
 __global__ void __launch_bounds__(AB_WARPS * 32, 1)
 k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ ready, uint32_t *__restrict__ done, uint32_t ring,
-             uint32_t n_b, unsigned long long *__restrict__ packed, unsigned long long *dbg) {
+             uint32_t n_b, unsigned long long *__restrict__ packed, unsigned long long *dbg, int prod) {
     using A = ACfg<SF>;
     extern __shared__ __align__(128) unsigned char ab_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
+    if (blockIdx.x >= n_b && prod == 2) {
+        ab_producer_groups<SF>(a, scratch, ready, done, ring, n_b, ab_raw, dbg);
+        return;
+    }
     if (blockIdx.x >= n_b) {
-        // ---- role A: warp items = U symbols x one block of 32 columns; the block of a warp never changes ---------
+        // ---- role A (version 1): warp items = U symbols x one block of 32 columns; the block of a warp never changes ---------
         // The 32 row pieces of an item (256 B each, one per lane) stream through the warp's own 2-slot TMA ring, so the
         // next item loads while this one is computed; 12 warps x 16 KiB in flight per SM.
         ABSmem &sa = *reinterpret_cast<ABSmem *>(ab_raw);

@@ -432,7 +432,9 @@ int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint3
     CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
     CU(cudaMemsetAsync(ready, 0, 2 * ring * sizeof(uint32_t), st));
     K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    k1_ab_kernel<SF><<<na + nb, AB_WARPS * 32, smem, st>>>(a, scratch, ready, done, ring, nb, d->d_packed, xg_watchdog_dev());
+    static const char *pv = getenv("LORA_B200_K1_AB_PROD");          // 2 = group producers (TMA in, in place, TMA out)
+    k1_ab_kernel<SF><<<na + nb, AB_WARPS * 32, smem, st>>>(a, scratch, ready, done, ring, nb, d->d_packed, xg_watchdog_dev(),
+                                                         pv && atoi(pv) == 2 ? 2 : 1);
     d->launches++;
     k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
     d->launches++;
