@@ -31,7 +31,7 @@ def run_variant(sf, env):
     (11, {"LORA_B200_K1_XCHG": "1"}),                                   # k1_xchg<11,256>: teams of 4
     (12, {"LORA_B200_K1_XCHG": "2", "LORA_B200_K1_XCHG_T": "128"}),     # k1_xchg<12,128>: teams of 16
     (12, {"LORA_B200_K1_SF12_GENERIC": "1"}),                           # the DIF-split k1_fft_kernel<12>
-    (12, {"LORA_B200_K1_AB": "2"}),                                     # k1_ab<12>: producer / consumer roles, radix 32
+    (12, {"LORA_B200_K1_AB": "2", "LORA_B200_K1_AB_NA": "64"}),         # k1_ab<12>: producer / consumer roles, radix 32
     (10, {"LORA_B200_K1_AB": "0", "LORA_B200_K1_AB_NA": "64"}),         # k1_ab<10>: radix 8, 4 symbols per producer item
 ])
 def test_k1_variant_matches_oracle(sf, env):
