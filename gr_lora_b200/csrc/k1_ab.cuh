@@ -17,8 +17,10 @@
 // Flags (global memory, monotonic): ready[slot] counts the 32 column blocks of the symbol in ring slot `slot` that role
 // A has stored (B waits for 32 * (s / K + 1) before it lets the TMA read row kc); done[slot] counts the rows role B has
 // pulled into shared memory (A waits for R * (s / K) before it overwrites the slot).  Every CTA of the grid is resident
-// (one per SM, sized by the shared memory of role B), so the waits cannot deadlock: the oldest unfinished symbol never
-// depends on a younger one.
+// (one per SM, sized by the shared memory of role B) and the ring is longer than the symbols a producer can hold
+// unpublished (launch_k1_ab), so the waits cannot deadlock: the oldest unfinished symbol never depends on a younger one.
+// tests/test_exchange_protocols.py runs the protocol as a model under random schedules (liveness at the bound, no torn
+// or overwritten buffer for any ring).
 #pragma once
 #include "k1_xchg.cuh"
 

@@ -413,7 +413,12 @@ int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint3
     // and still sit in the 126 MB L2 beside the streaming input
     static const char *rmb = getenv("LORA_B200_K1_AB_RING_MB");
     const size_t ring_mb = rmb && atoi(rmb) >= 8 ? (size_t)atoi(rmb) : 48;
-    const uint32_t ring = (uint32_t)((ring_mb << 20) / ((size_t)A::SPS * sizeof(float2)));
+    uint32_t ring = (uint32_t)((ring_mb << 20) / ((size_t)A::SPS * sizeof(float2)));
+    // liveness: a producer must never wait for a ring slot whose previous occupant it still holds unpublished; it holds
+    // at most two items of 32 / R symbols, consecutive symbols of one producer are 3 na / 8 apart
+    // (tests/test_exchange_protocols.py models the protocol and shows both the bound and what happens below it)
+    const uint32_t ring_min = 2u * (32u / A::R) * (3u * na / 8u) + 1u;
+    if (ring < ring_min) ring = ring_min;
     if (d->packed_cap < n_symbols) {
         if (d->d_packed) cudaFree(d->d_packed);
         d->d_packed = nullptr; d->packed_cap = 0;
