@@ -111,6 +111,7 @@ LB_HD unsigned long long ab_final(int lane, const W7Consts &c, const float2 *own
 
 #ifdef __CUDACC__
 constexpr int AB_WARPS = 12, AB_NSLOT = 2;
+constexpr int AB_FSTRIDE = 32;                           // uint32 per flag: one 128-byte line each (hot-spot relief)
 
 struct ABSmem {                                          // role B only
     float4 ones[W7_SLOT_F4];                             // "chirp" of the sub-problems: (1, 0)
@@ -128,10 +129,15 @@ LB_D uint32_t ab_flag_ld(const uint32_t *flag) {
     return v;
 }
 LB_D void ab_flag_add_relaxed(uint32_t *flag) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(flag) : "memory"); }
+// The first captures counted ~100 polls per consumer item, 1.7e10 polls/s from ~1800 warps on counters that sat in six
+// 128-byte lines: every flag now has a line of its own (AB_FSTRIDE) and a waiting warp backs off.
 LB_D void ab_spin(const uint32_t *flag, uint32_t need, unsigned long long *dbg, unsigned site, unsigned warp, unsigned sym) {
-    uint32_t spins = 0, got;
-    while ((got = ab_flag_ld(flag)) < need)
-        if (++spins == (1u << 18)) xg_dbg(dbg, site, 0, warp, sym, got);
+    uint32_t spins = 0, got, ns = 32;
+    while ((got = ab_flag_ld(flag)) < need) {
+        __nanosleep(ns);
+        if (ns < 1024) ns *= 2;
+        if (++spins == (1u << 14)) xg_dbg(dbg, site, 0, warp, sym, got);
+    }
 }
 
 LB_D void ab_bulk_s2g(void *dst_gmem, const void *src_smem, uint32_t bytes) {
@@ -222,7 +228,7 @@ LB_D void ab_producer_groups(const K1Args &a, float2 *scratch, uint32_t *ready, 
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const size_t s = sym_of(pend_item, u);
-                    if (s < a.n_symbols) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ready + (uint32_t)(s % ring)), "r"(GT / 32) : "memory");
+                    if (s < a.n_symbols) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ready + AB_FSTRIDE * (uint32_t)(s % ring)), "r"(GT / 32) : "memory");
                 }
             }
 #pragma unroll
@@ -230,7 +236,7 @@ LB_D void ab_producer_groups(const K1Args &a, float2 *scratch, uint32_t *ready, 
                 const size_t s = sym_of(item, u);
                 if (s >= a.n_symbols) break;
                 const uint32_t rs = (uint32_t)(s % ring);
-                ab_spin(done + rs, (uint32_t)(A::R * (s / ring)), dbg, 6, (unsigned)(threadIdx.x >> 5), (unsigned)s);
+                ab_spin(done + AB_FSTRIDE * rs, (uint32_t)(A::R * (s / ring)), dbg, 6, (unsigned)(threadIdx.x >> 5), (unsigned)s);
 #pragma unroll
                 for (int kc = 0; kc < A::R; kc++)
                     ab_bulk_s2g(scratch + ((size_t)rs * A::R + kc) * A::COLS + colbase, slot + (u * A::R + kc) * GT, 1024u);
@@ -249,7 +255,7 @@ LB_D void ab_producer_groups(const K1Args &a, float2 *scratch, uint32_t *ready, 
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const size_t s = sym_of(pend_item, u);
-            if (s < a.n_symbols) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ready + (uint32_t)(s % ring)), "r"(GT / 32) : "memory");
+            if (s < a.n_symbols) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ready + AB_FSTRIDE * (uint32_t)(s % ring)), "r"(GT / 32) : "memory");
         }
     }
     (void)lane;
@@ -317,7 +323,7 @@ k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ read
 #pragma unroll
             for (int u = 0; u < U; u++) {
                 const size_t s = first + (item * U + u) * step;
-                seen[u] = (lane == 0 && s < a.n_symbols) ? ab_flag_ld(done + (uint32_t)(s % ring)) : 0u;
+                seen[u] = (lane == 0 && s < a.n_symbols) ? ab_flag_ld(done + AB_FSTRIDE * (uint32_t)(s % ring)) : 0u;
             }
             xg_wait(&sa.bars[warp][si], (uint32_t)(item / AB_NSLOT) & 1u, dbg, 9, 0, (unsigned)warp, (unsigned)item);
 #pragma unroll
@@ -336,7 +342,7 @@ k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ read
                 ab_column_fft<SF>(c, v[u]);
                 const uint32_t rs = (uint32_t)(s % ring);
                 const uint32_t need = (uint32_t)(A::R * (s / ring));
-                if (lane == 0 && seen[u] < need) ab_spin(done + rs, need, dbg, 6, (unsigned)warp, (unsigned)s);
+                if (lane == 0 && seen[u] < need) ab_spin(done + AB_FSTRIDE * rs, need, dbg, 6, (unsigned)warp, (unsigned)s);
                 __syncwarp();
                 ab_column_store<SF>(scratch + (size_t)rs * A::SPS + col, v[u]);
                 pend[n_pend++] = rs;
@@ -345,7 +351,7 @@ k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ read
                 __syncwarp();
                 if (lane == 0) {
                     __threadfence();
-                    for (int u = 0; u < n_pend; u++) ab_flag_add_relaxed(ready + pend[u]);
+                    for (int u = 0; u < n_pend; u++) ab_flag_add_relaxed(ready + AB_FSTRIDE * pend[u]);
                 }
                 n_pend = 0;
             }
@@ -353,7 +359,7 @@ k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ read
         __syncwarp();
         if (lane == 0 && n_pend) {
             __threadfence();
-            for (int u = 0; u < n_pend; u++) ab_flag_add_relaxed(ready + pend[u]);
+            for (int u = 0; u < n_pend; u++) ab_flag_add_relaxed(ready + AB_FSTRIDE * pend[u]);
         }
         return;
     }
@@ -373,7 +379,7 @@ k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ read
     auto issue = [&](size_t u, int s) {                  // lane 0: wait for the 32 column blocks of the symbol, then load row kc
         const size_t sym = u / A::R;
         const uint32_t slot = (uint32_t)(sym % ring);
-        ab_spin(ready + slot, (uint32_t)(A::NBLK * (sym / ring + 1)), dbg, 7, (unsigned)warp, (unsigned)sym);
+        ab_spin(ready + AB_FSTRIDE * slot, (uint32_t)(A::NBLK * (sym / ring + 1)), dbg, 7, (unsigned)warp, (unsigned)sym);
         asm volatile("fence.proxy.async.global;" ::: "memory");     // role A's generic stores -> my async-proxy read
         mbar_expect_tx(&sm.bars[warp][s], 8192);
         bulk_g2s(sm.slots[warp][s], scratch + ((size_t)slot * A::R + (u % A::R)) * A::COLS, 8192, &sm.bars[warp][s]);
@@ -392,7 +398,7 @@ k1_ab_kernel(K1Args a, float2 *__restrict__ scratch, uint32_t *__restrict__ read
         const int s = it % AB_NSLOT;
         float4 *slot = sm.slots[warp][s];
         xg_wait(&sm.bars[warp][s], (it / AB_NSLOT) & 1u, dbg, 8, 0, (unsigned)warp, (unsigned)(u / A::R));
-        if (lane == 0) ab_flag_add_relaxed(done + (uint32_t)((u / A::R) % ring));   // the row is in shared memory: role A may reuse it
+        if (lane == 0) ab_flag_add_relaxed(done + AB_FSTRIDE * (uint32_t)((u / A::R) % ring));   // the row is in shared memory: role A may reuse it
         float2 v0[16], v1[16];
         w7_pass0(lane, slot, sm.ones, v0, v1);
         __syncwarp();

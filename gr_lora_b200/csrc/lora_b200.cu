@@ -425,7 +425,7 @@ int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint3
         CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
         d->packed_cap = n_symbols;
     }
-    const size_t xs_bytes = (size_t)ring * A::SPS * sizeof(float2) + 2 * ring * sizeof(uint32_t);
+    const size_t xs_bytes = (size_t)ring * A::SPS * sizeof(float2) + 2 * (size_t)ring * AB_FSTRIDE * sizeof(uint32_t);
     if (d->xs_cap < xs_bytes) {
         if (d->d_xs) cudaFree(d->d_xs);
         d->d_xs = nullptr; d->xs_cap = 0;
@@ -433,9 +433,9 @@ int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint3
         d->xs_cap = xs_bytes;
     }
     float2 *scratch = reinterpret_cast<float2 *>(d->d_xs);
-    uint32_t *ready = reinterpret_cast<uint32_t *>(scratch + (size_t)ring * A::SPS), *done = ready + ring;
+    uint32_t *ready = reinterpret_cast<uint32_t *>(scratch + (size_t)ring * A::SPS), *done = ready + (size_t)ring * AB_FSTRIDE;
     CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
-    CU(cudaMemsetAsync(ready, 0, 2 * ring * sizeof(uint32_t), st));
+    CU(cudaMemsetAsync(ready, 0, 2 * (size_t)ring * AB_FSTRIDE * sizeof(uint32_t), st));
     K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
     static const char *pv = getenv("LORA_B200_K1_AB_PROD");          // 2 = group producers (TMA in, in place, TMA out)
     k1_ab_kernel<SF><<<na + nb, AB_WARPS * 32, smem, st>>>(a, scratch, ready, done, ring, nb, d->d_packed, xg_watchdog_dev(),
