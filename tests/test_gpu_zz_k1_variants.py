@@ -1,4 +1,5 @@
-"""GPU parity of the opt-in K1 kernel variants.  The kernel choice is read from the environment once per process, so
+"""GPU parity of the opt-in K1 kernel variants (file name: runs after every other GPU test, so an experimental
+variant can never mask the default paths under `pytest -x`).  The kernel choice is read from the environment once per process, so
 each variant runs in its own interpreter (tools/k1_ab.py): bins bit-equal to the oracle on true symbols of that SF
 (ragged count, several grid passes, edge bins), magnitudes within 1e-4, every launch under the hang watchdog."""
 import json
