@@ -7,18 +7,25 @@
  * bench.py's cpu_baseline / --impl reference legs may load it; the product
  * (gr_lora_b200/, include/) never links, imports or calls anything in oracle/.
  *
- * Pinning status: the reference cannot be built here (GNU Radio, VOLK,
- * liquid-dsp, Boost absent), and it ships no IQ fixtures.  The oracle is pinned by
+ * Pinning status.  The reference ships no IQ fixtures and its cmake build needs GNU Radio, VOLK,
+ * liquid-dsp and Boost, none of which is installed.  This restatement is pinned by
+ *   - THE REFERENCE'S OWN CODE: oracle/_ref/liblora_ref.so is lib/decoder_impl.cc + lib/debugger.cc compiled
+ *     unmodified from /root/reference against stand-in headers for those libraries (oracle/ref_wrap.cc,
+ *     oracle/ref_standins/README.md).  tests/test_ref_pins_oracle.py requires restatement == reference, bit for bit,
+ *     for parameters, banner, chirp tables, instantaneous frequency, gradient demodulator, fine sync, the three
+ *     detectors, energy, deinterleave / deshuffle / dewhiten / Hamming / nibble order, and per work() call the state,
+ *     consume amount, bin, fine-sync correction, frames and stdout on the 13 golden cases, the SF x CR x payload
+ *     matrix of the reference's `short` suite, clock drift, frame offsets, CFO and noise; get_shift_fft bins equal
+ *     and magnitudes within fp32 FFT rounding.  tests/golden/golden.json is generated only if both agree,
  *   - the README console golden (README.md:62-71): banner numbers and the frame bytes
- *     " 04 90 40 de ad be ef 70 0d" reproduced through TX -> oracle (tests/test_oracle_golden.py),
+ *     " 04 90 40 de ad be ef 70 0d", through TX -> oracle and TX -> compiled reference,
  *   - the in-tree Hamming(8,4) code book (include/lora/utilities.h:257-264) and the
  *     single-error behaviour of hamming_decode_soft_byte (utilities.h:288-339),
  *   - the whitening tables' sha256 (lib/tables.h:30-44).
- * Intermediate values (bins, words, codewords) are pinned by nothing in the reference:
- * for those stages the parity claim is "GPU == this restatement", i.e. PARITY PARTIALLY
- * UNPINNED (Hamming: unpinned for >=2 bit errors per codeword, which depends on
- * liquid-dsp's table; FFT: any correct unnormalised forward DFT is equivalent within
- * fp32 rounding).
+ * Still unpinned, because it lives in the absent third-party libraries and not in the reference's source: the
+ * Hamming(8,4) decision for code words with >= 2 bit errors (liquid-dsp's table), the rounding of liquid's FFT (any
+ * correct unnormalised forward DFT is equivalent within fp32 rounding) and the summation order of VOLK's SIMD
+ * kernels (stand-in: generic protokernel order, which is also this file's order).
  *
  * Deliberate deviations where the reference has undefined behaviour:
  *   D1 fine_sync reads d_upchirp_ifreq_v past its end when bin==N-1 (decoder_impl.cc:310):

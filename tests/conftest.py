@@ -60,6 +60,35 @@ def make_case_iq(case, n_frames=2, cfo_hz=0.0):
     return x, fs, payload
 
 
+def make_capture(payload, sf, cr, crc, seed, n_frames=1, snr_db=38.0, lead=2.6, sfo_ppm=0.0, cfo_hz=0.0):
+    """Synthetic stand-in for one capture of the reference's test suites (apps/generate_test_suites.py:157-203):
+    explicit header, reduced rate above SF10, optional sampling-clock offset (ppm) and CFO.  Shared by the GPU parity
+    tests and the CPU test that pins the oracle to the compiled reference, so both see the same IQ."""
+    from gr_lora_b200 import tx
+    fsy = tx.encode_frame(payload, sf, cr, has_crc=crc, reduced_rate=sf > 10)
+    frame = tx.modulate_frame(fsy, sf, sync_word=0x78 if sf >= 11 else 0x12)
+    x = tx.channel([frame] * n_frames, sf=sf, snr_db=None, seed=seed, lead_symbols=lead, cfo_hz=cfo_hz).astype(np.complex128)
+    if sfo_ppm:
+        # transmitter clock off by sfo_ppm: resample by linear interpolation (band-limited enough at 8x oversampling)
+        t = np.arange(int(x.size / (1 + sfo_ppm * 1e-6))) * (1 + sfo_ppm * 1e-6)
+        i0 = np.floor(t).astype(np.int64)
+        fr = t - i0
+        i1 = np.minimum(i0 + 1, x.size - 1)
+        x = x[i0] * (1 - fr) + x[i1] * fr
+    x = x + tx.awgn(x.size, snr_db, np.random.default_rng(seed))
+    return x.astype(np.complex64)
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference's own decoder_impl.cc compiled against stand-in headers (oracle/_ref, oracle/ref.py)."""
+    from oracle import ref as R
+    if not R.available():
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    R.lib()
+    return R
+
+
 def case_decoder_args(case):
     name, sf, cr, implicit, crc, rr, payload_hex, snr, seed = case
     return dict(samp_rate=1e6, bandwidth=125000, sf=sf, implicit=implicit, cr=cr, crc=crc, reduced_rate=rr,

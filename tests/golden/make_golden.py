@@ -1,10 +1,13 @@
 #!/usr/bin/env python3
 """Regenerate tests/golden/golden.json.
 
-The reference ships no IQ fixtures and cannot be built here, so the golden
-vectors are: (1) the README console golden (README.md:62-71) and (2) outputs of the CPU
-oracle (oracle/, the line-by-line restatement of lib/decoder_impl.cc) on deterministic
-synthetic captures, recorded in THIS container.  Tests on any machine regenerate the same
+The reference ships no IQ fixtures, so the golden vectors are: (1) the README
+console golden (README.md:62-71) and (2) outputs recorded in THIS container on deterministic
+synthetic captures by the CPU oracle (oracle/lora_oracle.c, the restatement of
+lib/decoder_impl.cc) AND, where /root/reference is present, by the reference's own
+decoder_impl.cc compiled against stand-in headers (oracle/_ref, oracle/ref.py): generation
+fails unless both produce the same states, consume amounts, bins, frames and K1 bins, and the
+fixture then carries "pinned_by_reference": true.  Tests on any machine regenerate the same
 captures from the seeds and must reproduce these outputs with the oracle and with the GPU.
 
     python tests/golden/make_golden.py
@@ -22,6 +25,7 @@ sys.path.insert(0, str(HERE.parent))
 
 from conftest import FRAME_CASES, make_case_iq, case_decoder_args  # noqa: E402
 from oracle import oracle as O  # noqa: E402
+from oracle import ref as R  # noqa: E402
 from gr_lora_b200 import tx  # noqa: E402
 
 
@@ -37,12 +41,21 @@ def main():
     out = {"readme": {"banner": "Bits (nominal) per symbol: \t3.5\nBins per symbol: \t128\nSamples per symbol: \t1024\nDecimation: \t\t8\n",
                       "line": " 04 90 40 de ad be ef 70 0d", "source": "README.md:77-85 of the reference"},
            "frames": {}, "k1": {}}
+    have_ref = R.available()
+    out["pinned_by_reference"] = bool(have_ref)
+    out["reference_sources_sha256"] = (R.HERE / "_ref" / "SOURCES.sha256").read_text().split("\n") if have_ref and R.build() else []
     for case in FRAME_CASES:
         name = case[0]
         x, fs, payload = make_case_iq(case)
         d = O.Decoder(**case_decoder_args(case))
         consumed, steps = d.run(x)
         frames = d.frames()
+        if have_ref:      # the reference's own work() on the same capture (gradient demodulator, its live path)
+            r = R.RefDecoder(**case_decoder_args(case))
+            rc, rsteps = r.run(x)
+            assert rc == consumed and r.frames() == frames, name
+            for f in ("state", "consumed", "bin", "fine_sync"):
+                assert np.array_equal(steps[f], rsteps[f]), (name, f)
         out["frames"][name] = {
             "iq_sha256": hashlib.sha256(x.tobytes()).hexdigest(),
             "n_items": int(x.size),
@@ -61,6 +74,9 @@ def main():
         vals, x = k1_case(sf, n, 0.0, 1000 + sf)
         d = O.Decoder(sf=sf)
         fb, fm = d.demod_fft_batch(x)
+        if have_ref:      # the reference's get_shift_fft (lib/decoder_impl.cc:430-464) on the same symbols
+            rb, rm = R.RefDecoder(sf=sf).demod_fft_batch(x)
+            assert np.array_equal(rb, fb) and np.allclose(rm, fm, rtol=2e-5), sf
         gb = d.demod_grad_batch(tx.synth_symbols(vals, sf))          # gradient demod needs a clean input
         out["k1"][str(sf)] = {"n": n, "snr_db": 0.0, "seed": 1000 + sf, "values": [int(v) for v in vals],
                               "fft_bins": [int(b) for b in fb], "fft_mags": [float(m) for m in fm],

@@ -18,20 +18,9 @@ def torch():
     return torch
 
 
-def _capture(payload, sf, cr, crc, seed, n_frames=1, snr_db=38.0, lead=2.6, sfo_ppm=0.0, cfo_hz=0.0):
-    from gr_lora_b200 import tx
-    fsy = tx.encode_frame(payload, sf, cr, has_crc=crc, reduced_rate=sf > 10)
-    frame = tx.modulate_frame(fsy, sf, sync_word=0x78 if sf >= 11 else 0x12)
-    x = tx.channel([frame] * n_frames, sf=sf, snr_db=None, seed=seed, lead_symbols=lead, cfo_hz=cfo_hz).astype(np.complex128)
-    if sfo_ppm:
-        # transmitter clock off by sfo_ppm: resample by linear interpolation (band-limited enough at 8x oversampling)
-        t = np.arange(int(x.size / (1 + sfo_ppm * 1e-6))) * (1 + sfo_ppm * 1e-6)
-        i0 = np.floor(t).astype(np.int64)
-        fr = t - i0
-        i1 = np.minimum(i0 + 1, x.size - 1)
-        x = x[i0] * (1 - fr) + x[i1] * fr
-    x = x + tx.awgn(x.size, snr_db, np.random.default_rng(seed))
-    return x.astype(np.complex64)
+def _capture(*args, **kw):
+    from conftest import make_capture
+    return make_capture(*args, **kw)
 
 
 def _both(oracle, x, sf, cr, crc, demod="gradient", trace=True):

@@ -14,6 +14,13 @@ from gr_lora_b200 import tx, whitening
 GOLD = json.loads((Path(__file__).parent / "golden" / "golden.json").read_text())
 
 
+def test_fixture_was_checked_against_the_compiled_reference():
+    """tests/golden/make_golden.py refuses to write the fixture unless oracle/_ref (the reference's own
+    lib/decoder_impl.cc) reproduces every recorded state, consume amount, bin and frame."""
+    assert GOLD["pinned_by_reference"] is True
+    assert any("decoder_impl.cc" in ln for ln in GOLD["reference_sources_sha256"])
+
+
 def test_readme_banner_and_frames(oracle):
     """README.md:77-85: banner for SF7 BW125k @1 MS/s and ' 04 90 40 de ad be ef 70 0d' x5."""
     d = oracle.Decoder(sf=7, cr=4, crc=True)
