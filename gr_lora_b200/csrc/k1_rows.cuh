@@ -1,0 +1,612 @@
+// k1_rows.cuh -- K1 (dechirp + pruned FFT + argmax, lib/decoder_impl.cc:430-464) for SF11 and SF12.
+//
+// What bounds the large spreading factors (measured in round 1 and re-derived from the microarchitecture notes): one
+// symbol is 128 / 256 KiB, every organisation that moves intermediate data BETWEEN SMs pays for it -- the exchange through
+// L2 triples the L2 traffic and the L2 slices deliver only about one HBM bandwidth in total (k1_xchg, k1_ab: <= 1/3),
+// DSMEM moves ~20 B/clk per SM (k1_cluster, k1_big), and splitting the DFT by output residue re-reads the input.  This
+// kernel keeps every sample of a symbol inside ONE SM from its TMA load to the argmax:
+//
+//   * the 8 polyphase branches (n = 8 n1 + r) are independent L-point FFTs (L = N = 2^SF).  SF11: one CTA per symbol, all 8
+//     branches (8 x 2048 points = 128 KiB).  SF12: a cluster of two CTAs per symbol, CTA c takes branches 4c .. 4c+3 (4 x 4096
+//     points = 128 KiB, the 32-byte halves of every 64-byte group of samples, fetched with a 2-D tensor-map TMA so that L2
+//     delivers every sector once); the only data that crosses SMs is one partial sum per output bin (16 KiB per symbol
+//     and direction, DSMEM) -- 1/16 of the symbol.
+//   * a symbol is 16 ROWS of 8 KiB (row j = n1 in [j L/16, (j+1) L/16), all local branches).  Rows live in a pool of
+//     28 (26) shared-memory slots of 8 KiB that rotates: global row g of this CTA's symbol sequence sits in slot g mod P.
+//     16 slots hold the symbol being transformed, the others receive the next rows by TMA while it is; a slot is
+//     re-armed by the warp that finished with it.  All three FFT passes are IN PLACE, so shared-memory traffic is
+//     6 x 8 B per sample (TMA write, three read-modify passes): 48 B against the 128 B/clk crossbar = 0.8 of the HBM
+//     roofline; there is no room (and no need) for a second copy of anything.
+//   * the dechirp table (128 KiB per CTA) and the inter-pass twiddles do not fit in shared memory next to that and
+//     re-reading them through L2 would double the L2 traffic.  They are thread-invariant (a thread always handles the
+//     same sample positions), so they live in TENSOR MEMORY: written once per CTA with tcgen05.st, read back per symbol
+//     with tcgen05.ld (TMEM is otherwise idle in this library: the path has no matrix product).
+//   * pass structure per symbol (512 threads = 16 warps, ONE CTA barrier per symbol):
+//       pass 0  warp a1, lane (a0, p): float4 #(a, p) of each of the 16 rows -> dechirp -> two radix-16 DIFs over the rows
+//               -> twiddle W_L^{a kc} -> written back to row kc (in place; 16-byte units XOR-swizzled by a1 & 7 inside
+//               the warp's own 512-byte block, so no other warp's data is touched)                       __syncthreads
+//       pass 1  warp kc, lane (a0, p): radix-16 over a1 inside row kc -> twiddle W_{L/16}^{a0 kb} -> in place    __syncwarp
+//       pass 2  warp kc, lane (kb, h): radix-(L/256) over a0 for half of the local branches -> Horner over the branches with
+//               W_sps^{k'} -> lane-pair exchange -> [SF12: partial sums to / from the peer CTA] -> |.|^2 -> argmax
+//               -> the warp re-arms its slot with the row that maps to it P rows later.
+//     bin k = kc + 16 kb + 256 q2.  Same arithmetic as get_shift_fft including tmp[N/2] += F[N/2] and the first-maximum
+//     tie break; bins are bit-equal to the oracle's on the parity inputs, magnitudes within fp32 rounding.
+// The index arithmetic and the butterflies are __host__ __device__ (r_emulate below runs them on the CPU for the
+// non-GPU tests, with shared memory, tensor memory and the peer exchange modelled as plain arrays).
+#pragma once
+#include "k1_warp.cuh"
+
+namespace lb {
+
+template <int SF>
+struct RCfg {
+    static constexpr int N = 1 << SF, SPS = 8 * N, L = N;
+    static constexpr int CL = SF == 12 ? 2 : 1;          // CTAs per symbol
+    static constexpr int NB = 8 / CL;                    // branches per CTA
+    static constexpr int A = L / 16;                     // n1 values per row: 128 / 256
+    static constexpr int A0 = L / 256;                   // points of the last pass: 8 / 16
+    static constexpr int CPA = NB / 2;                   // 16-byte units (branch pairs) per n1: 4 / 2
+    static constexpr int ROW_F4 = A * CPA;               // 512 float4 = 8 KiB
+    static constexpr uint32_t ROW_BYTES = 8192u;
+    static constexpr int NSLOT = SF == 12 ? 26 : 28;     // slot pool (SF12 gives 16 KiB to the peer-exchange buffer)
+    static constexpr int T = 512, NW = 16;
+    static constexpr int HB = NB / 2;                    // branches per lane in pass 2: 4 / 2
+    static_assert(SF == 11 || SF == 12, "rows kernel: SF11, SF12");
+    static_assert(A0 * CPA == 32, "one warp = one a1 block of every row");
+};
+
+constexpr int R_NSYM_BAR = 4;                            // symbol barriers in rotation (<= 2.75 symbols in flight)
+
+// tensor-memory columns of one thread (lane = 32 (warp & 3) + lane):
+//   chirp   [64 (warp >> 2), +64)        c[j][b] of the thread's pass-0 samples, word 4 j + 2 b + {re, im}
+//   tw0     [256 + 32 (warp >> 2), +32)  W_L^{a kc}, kc = 1..15, word 2 (kc - 1) + {re, im}
+//   tw1     [384, +32)                   W_{L/16}^{a0 kb}, kb = 1..15 (a function of the lane only: shared by 4 warps)
+constexpr int R_TM_COLS = 512, R_TM_CHIRP = 0, R_TM_TW0 = 256, R_TM_TW1 = 384;
+
+// ---- index arithmetic --------------------------------------------------------------------------------------------------
+template <int SF> LB_HD int r_a0(int lane) { return lane / RCfg<SF>::CPA; }
+template <int SF> LB_HD int r_p(int lane) { return lane % RCfg<SF>::CPA; }
+// sample index of the first of the two samples (branches 2p, 2p+1 of this CTA) a pass-0 thread reads from row j
+template <int SF> LB_HD int r_sample(int rank, int warp, int lane, int j) {
+    using C = RCfg<SF>;
+    const int a = warp * C::A0 + r_a0<SF>(lane);
+    return 8 * (j * C::A + a) + rank * C::NB + 2 * r_p<SF>(lane);
+}
+LB_HD int r_unit(int block, int within) { return block * 32 + (within ^ (block & 7)); }   // swizzled float4 index in a row
+template <int SF> LB_HD int r_signed_bin(int k) { return k < RCfg<SF>::L / 2 ? k : k - RCfg<SF>::L; }
+// exponent (mod sps) of the per-q2 factor of W_sps^{e k'}: k' = kc + 16 kb + 256 q2 - (q2 >= A0/2 ? L : 0)
+template <int SF> LB_HD int r_cq_exp(int e, int q2) {
+    using C = RCfg<SF>;
+    const int d = 256 * q2 - (q2 >= C::A0 / 2 ? C::L : 0);
+    return (e * d) & (C::SPS - 1);
+}
+
+struct RConsts {            // per-q2 factors, [e index][q2]; SF11: e = 1, 4; SF12: e = 1, 2, 4, 6
+    float2 cq[4][16];
+};
+template <int SF> LB_HD int r_e_of(int i) { return SF == 11 ? (i == 0 ? 1 : 4) : (i == 0 ? 1 : 2 * i); }
+template <int SF>
+inline void r_build_consts(const float2 *tw_host, RConsts &c) {
+    for (int i = 0; i < 4; i++)
+        for (int q2 = 0; q2 < 16; q2++) c.cq[i][q2] = tw_host[r_cq_exp<SF>(r_e_of<SF>(i), q2 % RCfg<SF>::A0)];
+}
+
+// ---- pass 0 / pass 1 arithmetic on registers -----------------------------------------------------------------------------
+// v0 / v1: the two branches of the thread's float4 column, 16 points each; tw[kc - 1] the output twiddles
+LB_HD void r_dif16_twiddle(float2 *v0, float2 *v1, const float2 *tw) {
+    dft_dif<16>(v0);
+    dft_dif<16>(v1);
+#pragma unroll
+    for (int k = 1; k < 16; k++) {
+        const int br = bitrev<16>(k);
+        v0[br] = cmul(v0[br], tw[k - 1]);
+        v1[br] = cmul(v1[br], tw[k - 1]);
+    }
+}
+
+// ---- pass 2 arithmetic ----------------------------------------------------------------------------------------------------
+// g[b][.]: A0 points of local branch (HB h + b); after the DFT g[b][bitrev(q2)] = G_r[kc + 16 kb + 256 q2].
+// Returns in t[q2] this lane's share of the sum over the branches, already multiplied by the power of w that places
+// it:  t[q2] = w^{E} * sum_b w^b g[b][q2],  E = global index of the lane's first branch,  w = W_sps^{k'(q2)}.
+// wb1 = W_sps^{kc + 16 kb}, wbE = W_sps^{E (kc + 16 kb)};  cq1 / cqE the per-q2 factors (RConsts rows).
+template <int SF>
+LB_HD void r_pass2_sum(float2 (*g)[RCfg<SF>::A0], int E, float2 wb1, float2 wbE, const float2 *cq1, const float2 *cqE, float2 *t) {
+    using C = RCfg<SF>;
+#pragma unroll
+    for (int b = 0; b < C::HB; b++) dft_dif<C::A0>(g[b]);
+#pragma unroll
+    for (int q2 = 0; q2 < C::A0; q2++) {
+        const int br = bitrev<C::A0>(q2);
+        const float2 w = cmul(wb1, cq1[q2]);
+        float2 acc = g[C::HB - 1][br];
+#pragma unroll
+        for (int b = C::HB - 2; b >= 0; b--) acc = cfma(acc, w, g[b][br]);
+        t[q2] = E ? cmul(acc, cmul(wbE, cqE[q2])) : acc;
+    }
+}
+// the second evaluation of bin N/2 (tmp[N/2] += F[N/2], :450): same G values, conjugate twiddles (W_sps^{+N/2 r})
+template <int SF>
+LB_HD float2 r_pass2_quirk(float2 (*g)[RCfg<SF>::A0], int E, float2 wb1, float2 wbE, const float2 *cq1, const float2 *cqE) {
+    using C = RCfg<SF>;
+    const int q2 = C::A0 / 2, br = bitrev<C::A0>(q2);
+    const float2 w = cconj(cmul(wb1, cq1[q2]));
+    float2 acc = g[C::HB - 1][br];
+#pragma unroll
+    for (int b = C::HB - 2; b >= 0; b--) acc = cfma(acc, w, g[b][br]);
+    return E ? cmul(acc, cconj(cmul(wbE, cqE[q2]))) : acc;
+}
+
+#ifdef __CUDACC__
+// ---- tensor memory ---------------------------------------------------------------------------------------------------------
+LB_D void tm_alloc(uint32_t *smem_dst) {      // one warp; R_TM_COLS columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(R_TM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+LB_D void tm_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(R_TM_COLS) : "memory");
+}
+LB_D void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+LB_D void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+LB_D void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+LB_D void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 16 consecutive columns of the thread's lane <-> 8 complex values
+LB_D void tm_st16(uint32_t taddr, const float2 *v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
+                 "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y) : "memory");
+}
+LB_D void tm_ld16(uint32_t taddr, float2 *v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
+                   "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
+                 : "r"(taddr) : "memory");
+}
+
+// ---- cluster helpers (SF12) -----------------------------------------------------------------------------------------------
+LB_D uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+LB_D uint32_t map_to_peer(uint32_t local_smem_addr, uint32_t peer) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(peer));
+    return r;
+}
+LB_D void st_peer_f4(uint32_t peer_addr, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(peer_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+LB_D void st_peer_f2(uint32_t peer_addr, float2 v) {
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(peer_addr), "f"(v.x), "f"(v.y) : "memory");
+}
+LB_D void mbar_arrive_peer(uint32_t peer_bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar_addr) : "memory");
+}
+LB_D void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // acquire at cluster scope: the peer's DSMEM stores are visible after it
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+LB_D void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
+LB_D void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// 2-D tensor-map TMA: box {8 floats (the CTA's 4 branches of one n1), 256 n1} -> 8 KiB, dense in shared memory
+LB_D void tma_rows_2d(void *dst_smem, const void *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int SF>
+struct RSmem {
+    float4 slots[RCfg<SF>::NSLOT][RCfg<SF>::ROW_F4];
+    float2 recv[RCfg<SF>::CL == 2 ? 2048 + 8 : 8];      // peer partial sums [kc & 7][kb][h][8] (+ the bin-N/2 extra), SF12 only
+    unsigned long long keys[2][RCfg<SF>::NW];
+    uint64_t sym_full[R_NSYM_BAR];
+    uint64_t x_full[8], x_free[8];                        // SF12: per receiving / sending warp pair
+    uint32_t tm_base;
+};
+
+struct RParams {
+    K1Args a;
+    const void *tmap;                  // SF12: CUtensorMap of the IQ batch, in global memory
+    unsigned long long *packed;        // SF12: per-symbol argmax keys merged by atomicMax (finalised by k1_finalize_kernel)
+    uint32_t *bins;                    // SF11: written directly
+    float *mags;
+};
+
+__device__ __constant__ RConsts r_consts_dev[2];          // [SF - 11]
+
+template <int SF>
+__global__ void __launch_bounds__(RCfg<SF>::T, 1)
+k1_rows_kernel(const __grid_constant__ RParams P) {
+    using C = RCfg<SF>;
+    extern __shared__ __align__(1024) unsigned char r_raw[];
+    RSmem<SF> &sm = *reinterpret_cast<RSmem<SF> *>(r_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t rank = C::CL == 2 ? cluster_rank() : 0u, peer = rank ^ 1u;
+    const size_t unit = blockIdx.x / C::CL, n_units = gridDim.x / C::CL;        // symbol sequence of this CTA (cluster)
+    const K1Args &a = P.a;
+    const size_t n_mine = unit < a.n_symbols ? (a.n_symbols - unit + n_units - 1) / n_units : 0;
+    const RConsts &rc = r_consts_dev[SF - 11];
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < R_NSYM_BAR; i++) mbar_init(&sm.sym_full[i], 16);
+#pragma unroll
+        for (int i = 0; i < 8; i++) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_free[i], 1); }
+        fence_mbar_init();
+    }
+    if (warp == 0) tm_alloc(&sm.tm_base);
+    tm_fence_before();
+    __syncthreads();
+    tm_fence_after();
+    const uint32_t tm_lane = sm.tm_base + ((uint32_t)(32 * (warp & 3)) << 16);
+
+    // issue of global row g of this CTA's sequence (symbol g / 16, row g % 16) into slot g % NSLOT
+    auto issue_row = [&](size_t g) {
+        const size_t s = g >> 4;
+        if (s >= n_mine) return;
+        const int j = (int)(g & 15);
+        const size_t sym = unit + s * n_units;
+        uint64_t *bar = &sm.sym_full[s % R_NSYM_BAR];
+        float4 *dst = sm.slots[g % C::NSLOT];
+        mbar_expect_tx(bar, C::ROW_BYTES);
+        if (C::CL == 1) bulk_g2s(dst, a.x + sym * C::SPS + (size_t)j * (C::SPS / 16), C::ROW_BYTES, bar);
+        else tma_rows_2d(dst, P.tmap, (int)(rank * 8u), (int)(sym * C::L + (size_t)j * C::A), bar);
+    };
+    if (tid == 0)
+        for (int g = 0; g < C::NSLOT; g++) issue_row((size_t)g);
+
+    // ---- thread-invariant tables into tensor memory -------------------------------------------------------------------
+    {
+        float2 buf[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {                     // chirp: rows 4q .. 4q+3, two samples each
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const float4 c4 = k1_ld_table4(a.chirp + r_sample<SF>((int)rank, warp, lane, 4 * q + jj));
+                buf[2 * jj] = make_float2(c4.x, c4.y);
+                buf[2 * jj + 1] = make_float2(c4.z, c4.w);
+            }
+            tm_st16(tm_lane + (uint32_t)(R_TM_CHIRP + 64 * (warp >> 2) + 16 * q), buf);
+        }
+        const int a_idx = warp * C::A0 + r_a0<SF>(lane);
+#pragma unroll
+        for (int q = 0; q < 2; q++) {                     // tw0[kc - 1] = W_L^{a kc} = W_sps^{8 a kc}
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int kc = 8 * q + i + 1;
+                buf[i] = kc < 16 ? k1_ld_table(a.tw + ((8 * a_idx * kc) & (C::SPS - 1))) : make_float2(0.f, 0.f);
+            }
+            tm_st16(tm_lane + (uint32_t)(R_TM_TW0 + 32 * (warp >> 2) + 16 * q), buf);
+        }
+        if (warp < 4) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {                 // tw1[kb - 1] = W_{L/16}^{a0 kb} = W_sps^{128 a0 kb}
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int kb = 8 * q + i + 1;
+                    buf[i] = kb < 16 ? k1_ld_table(a.tw + ((128 * r_a0<SF>(lane) * kb) & (C::SPS - 1))) : make_float2(0.f, 0.f);
+                }
+                tm_st16(tm_lane + (uint32_t)(R_TM_TW1 + 16 * q), buf);
+            }
+        }
+        tm_wait_st();
+    }
+    // pass-2 lane constants: kc = warp, kb = lane >> 1, h = lane & 1; E = global index of the lane's first branch
+    const int kb2 = lane >> 1, h2 = lane & 1;
+    const int E2 = (int)rank * C::NB + h2 * C::HB;
+    const int e_idx = SF == 11 ? (E2 ? 1 : 0) : (E2 >> 1);            // row of RConsts::cq for w^E (unused when E == 0)
+    const float2 wb1 = k1_ld_table(a.tw + ((warp + 16 * kb2) & (C::SPS - 1)));
+    const float2 wbE = k1_ld_table(a.tw + ((E2 * (warp + 16 * kb2)) & (C::SPS - 1)));
+    tm_fence_before();
+    if (C::CL == 2) cluster_sync_all(); else __syncthreads();     // tw1 columns of warps 0-3 are read by every warp; peers' barriers are initialised
+    tm_fence_after();
+
+    for (size_t s = 0; s < n_mine; s++) {
+        const size_t sym = unit + s * n_units;
+        const size_t g0 = s * 16;
+        mbar_wait(&sm.sym_full[s % R_NSYM_BAR], (uint32_t)((s / R_NSYM_BAR) & 1));
+
+        // ---- pass 0: radix 16 over the rows, warp = a1 block -----------------------------------------------------------
+        {
+            float2 v0[16], v1[16], tw[16];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                float2 ch[8];
+                tm_ld16(tm_lane + (uint32_t)(R_TM_CHIRP + 64 * (warp >> 2) + 16 * q), ch);
+                float4 xv[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) xv[jj] = sm.slots[(g0 + 4 * q + jj) % C::NSLOT][warp * 32 + lane];
+                tm_wait_ld();
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    v0[4 * q + jj] = cmul(make_float2(xv[jj].x, xv[jj].y), ch[2 * jj]);
+                    v1[4 * q + jj] = cmul(make_float2(xv[jj].z, xv[jj].w), ch[2 * jj + 1]);
+                }
+            }
+            tm_ld16(tm_lane + (uint32_t)(R_TM_TW0 + 32 * (warp >> 2)), tw);
+            tm_ld16(tm_lane + (uint32_t)(R_TM_TW0 + 32 * (warp >> 2) + 16), tw + 8);
+            tm_wait_ld();
+            r_dif16_twiddle(v0, v1, tw);
+#pragma unroll
+            for (int kc = 0; kc < 16; kc++) {
+                const int br = bitrev<16>(kc);
+                sm.slots[(g0 + kc) % C::NSLOT][r_unit(warp, lane)] = make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y);
+            }
+        }
+        __syncthreads();
+        // result of the previous symbol (its keys were complete before this barrier)
+        if (s > 0 && warp == 0) {
+            unsigned long long k = lane < C::NW ? sm.keys[(s - 1) & 1][lane] : 0ull;
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
+                k = o > k ? o : k;
+            }
+            if (lane == 0) {
+                const size_t psym = unit + (s - 1) * n_units;
+                if (C::CL == 2) atomicMax(P.packed + psym, k);
+                else { P.bins[psym] = key_idx(k); if (P.mags) P.mags[psym] = sqrtf(key_mag2(k)); }
+            }
+        }
+        float4 *row = sm.slots[(g0 + warp) % C::NSLOT];
+        // ---- pass 1: radix 16 over a1 inside row kc = warp -------------------------------------------------------------
+        {
+            float2 v0[16], v1[16], tw[16];
+            tm_ld16(sm.tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)R_TM_TW1, tw);
+            tm_ld16(sm.tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(R_TM_TW1 + 16), tw + 8);
+#pragma unroll
+            for (int a1 = 0; a1 < 16; a1++) {
+                const float4 u = row[r_unit(a1, lane)];
+                v0[a1] = make_float2(u.x, u.y);
+                v1[a1] = make_float2(u.z, u.w);
+            }
+            tm_wait_ld();
+            r_dif16_twiddle(v0, v1, tw);
+#pragma unroll
+            for (int kb = 0; kb < 16; kb++) {
+                const int br = bitrev<16>(kb);
+                row[r_unit(kb, lane)] = make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y);
+            }
+        }
+        __syncwarp();
+        // ---- pass 2: radix A0 over a0, branch sum, argmax ---------------------------------------------------------------
+        unsigned long long best = 0ull;
+        {
+            float2 g[C::HB][C::A0], t[C::A0];
+            if (SF == 11) {
+#pragma unroll
+                for (int a0 = 0; a0 < C::A0; a0++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const float4 u = row[r_unit(kb2, a0 * 4 + 2 * h2 + e)];
+                        g[2 * e][a0] = make_float2(u.x, u.y);
+                        g[(2 * e + 1) % C::HB][a0] = make_float2(u.z, u.w);
+                    }
+            } else {
+#pragma unroll
+                for (int a0 = 0; a0 < C::A0; a0++) {
+                    const float4 u = row[r_unit(kb2, a0 * 2 + h2)];
+                    g[0][a0] = make_float2(u.x, u.y);
+                    g[C::HB - 1][a0] = make_float2(u.z, u.w);
+                }
+            }
+            const bool quirk_warp = warp == 0;                       // bin N/2 = (kc 0, kb 0, q2 A0/2): lanes 0 and 1 of warp 0
+            float2 tq = make_float2(0.f, 0.f);
+            if (quirk_warp && kb2 == 0) tq = r_pass2_quirk<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx]);
+            r_pass2_sum<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx], t);
+            // lane pair: h = 0 keeps q2 < A0/2, h = 1 keeps q2 >= A0/2; each sends the other half
+            float2 f[C::A0 / 2];
+#pragma unroll
+            for (int i = 0; i < C::A0 / 2; i++) {
+                const float2 give = h2 ? t[i] : t[i + C::A0 / 2];
+                const float2 keep = h2 ? t[i + C::A0 / 2] : t[i];
+                float2 got;
+                got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
+                got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
+                f[i] = cadd(keep, got);
+            }
+            if (quirk_warp) {                                          // both halves of the conjugate evaluation end up in lane 1
+                float2 got;
+                got.x = __shfl_xor_sync(0xffffffffu, tq.x, 1);
+                got.y = __shfl_xor_sync(0xffffffffu, tq.y, 1);
+                tq = cadd(tq, got);
+            }
+            if (C::CL == 2) {
+                // bins of rows kc < 8 are finished by CTA 0, kc >= 8 by CTA 1: the other CTA sends its partial sums
+                const int xi = warp & 7;
+                const bool mine = (uint32_t)(warp >> 3) == rank;
+                const int ridx = ((xi * 16 + kb2) * 2 + h2) * 8;
+                if (!mine) {
+                    if (s > 0) mbar_wait_cluster(&sm.x_free[xi], (uint32_t)((s - 1) & 1));     // the peer has read the previous symbol's sums
+                    const uint32_t dst = map_to_peer(smem_u32(&sm.recv[ridx]), peer);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) st_peer_f4(dst + 16u * i, make_float4(f[2 * i].x, f[2 * i].y, f[2 * i + 1].x, f[2 * i + 1].y));
+                    if (quirk_warp && lane == 1) st_peer_f2(map_to_peer(smem_u32(&sm.recv[2048]), peer), tq);
+                    fence_cluster();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_peer(map_to_peer(smem_u32(&sm.x_full[xi]), peer));
+                } else {
+                    mbar_wait_cluster(&sm.x_full[xi], (uint32_t)(s & 1));
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float4 u = *reinterpret_cast<const float4 *>(&sm.recv[ridx + 2 * i]);
+                        f[2 * i] = cadd(f[2 * i], make_float2(u.x, u.y));
+                        f[2 * i + 1] = cadd(f[2 * i + 1], make_float2(u.z, u.w));
+                    }
+                    if (quirk_warp && lane == 1) tq = cadd(tq, sm.recv[2048]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_peer(map_to_peer(smem_u32(&sm.x_free[xi]), peer));
+                }
+                if (mine) {
+                    if (quirk_warp && lane == 1) f[0] = cadd(f[0], tq);
+#pragma unroll
+                    for (int i = 0; i < C::A0 / 2; i++) {
+                        const int q2 = i + h2 * (C::A0 / 2);
+                        const unsigned long long key = pack_key(cnorm2(f[i]), (uint32_t)(warp + 16 * kb2 + 256 * q2));
+                        best = key > best ? key : best;
+                    }
+                }
+            } else {
+                if (quirk_warp && lane == 1) f[0] = cadd(f[0], tq);
+#pragma unroll
+                for (int i = 0; i < C::A0 / 2; i++) {
+                    const int q2 = i + h2 * (C::A0 / 2);
+                    const unsigned long long key = pack_key(cnorm2(f[i]), (uint32_t)(warp + 16 * kb2 + 256 * q2));
+                    best = key > best ? key : best;
+                }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
+            best = o > best ? o : best;
+        }
+        // every lane is done with the row (the shuffles above are the warp's convergence point): re-arm its slot
+        if (lane == 0) {
+            sm.keys[s & 1][warp] = best;
+            fence_proxy_async();
+            issue_row(g0 + (size_t)warp + (size_t)C::NSLOT);
+        }
+    }
+    __syncthreads();
+    if (n_mine > 0 && warp == 0) {
+        unsigned long long k = lane < C::NW ? sm.keys[(n_mine - 1) & 1][lane] : 0ull;
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
+            k = o > k ? o : k;
+        }
+        if (lane == 0) {
+            const size_t psym = unit + (n_mine - 1) * n_units;
+            if (C::CL == 2) atomicMax(P.packed + psym, k);
+            else { P.bins[psym] = key_idx(k); if (P.mags) P.mags[psym] = sqrtf(key_mag2(k)); }
+        }
+    }
+    tm_fence_before();
+    if (C::CL == 2) cluster_sync_all(); else __syncthreads();     // no CTA of the pair exits while the other may still store into it
+    tm_fence_after();
+    if (warp == 0) tm_dealloc(sm.tm_base);
+}
+#endif  // __CUDACC__
+
+// ---- CPU emulation of the same index arithmetic (tests/test_host_emulation.py) ---------------------------------------------------
+// Shared memory slots, the tensor-memory tables and the peer exchange are plain arrays; the threads of a pass run one after
+// the other (legal: a pass only reads what the previous barrier made visible, and its in-place writes stay inside the
+// thread's own units -- the emulation asserts that by poisoning).
+template <int SF>
+inline void r_emulate(const K1Args &a, uint32_t *bins, float *mags) {
+    using C = RCfg<SF>;
+    RConsts rc;
+    r_build_consts<SF>(a.tw, rc);
+    const int NSL = C::NSLOT;
+    float4 *slots[2];
+    float2 *part[2];
+    for (int c = 0; c < C::CL; c++) { slots[c] = new float4[(size_t)NSL * C::ROW_F4]; part[c] = new float2[C::L + 1]; }
+    unsigned long long *keys = new unsigned long long[C::CL * C::NW];
+    for (size_t s = 0; s < a.n_symbols; s++) {
+        const float2 *x = a.x + s * C::SPS;
+        const size_t g0 = s * 16;
+        for (int c = 0; c < C::CL; c++) {
+            float4 *sl = slots[c];
+            auto slot = [&](size_t g) { return sl + (g % NSL) * C::ROW_F4; };
+            for (int j = 0; j < 16; j++)                         // TMA: row j, natural order
+                for (int aa = 0; aa < C::A; aa++)
+                    for (int p = 0; p < C::CPA; p++) {
+                        const int n = 8 * (j * C::A + aa) + c * C::NB + 2 * p;
+                        slot(g0 + j)[aa * C::CPA + p] = make_float4(x[n].x, x[n].y, x[n + 1].x, x[n + 1].y);
+                    }
+            for (int warp = 0; warp < C::NW; warp++) {           // pass 0 (a warp's reads all precede its writes)
+                float2 v0[32][16], v1[32][16];
+                for (int lane = 0; lane < 32; lane++) {
+                    float2 tw[16];
+                    const int a_idx = warp * C::A0 + r_a0<SF>(lane);
+                    for (int kc = 1; kc < 16; kc++) tw[kc - 1] = a.tw[(8 * a_idx * kc) & (C::SPS - 1)];
+                    for (int j = 0; j < 16; j++) {
+                        const float4 xv = slot(g0 + j)[warp * 32 + lane];
+                        const int n = r_sample<SF>(c, warp, lane, j);
+                        v0[lane][j] = cmul(make_float2(xv.x, xv.y), a.chirp[n]);
+                        v1[lane][j] = cmul(make_float2(xv.z, xv.w), a.chirp[n + 1]);
+                    }
+                    r_dif16_twiddle(v0[lane], v1[lane], tw);
+                }
+                for (int lane = 0; lane < 32; lane++)
+                    for (int kc = 0; kc < 16; kc++) {
+                        const int br = bitrev<16>(kc);
+                        slot(g0 + kc)[r_unit(warp, lane)] = make_float4(v0[lane][br].x, v0[lane][br].y, v1[lane][br].x, v1[lane][br].y);
+                    }
+            }
+            for (int warp = 0; warp < C::NW; warp++) {           // pass 1 + pass 2 of row kc = warp
+                float4 *row = slot(g0 + warp);
+                float2 v0[32][16], v1[32][16];
+                for (int lane = 0; lane < 32; lane++) {
+                    float2 tw[16];
+                    for (int kb = 1; kb < 16; kb++) tw[kb - 1] = a.tw[(128 * r_a0<SF>(lane) * kb) & (C::SPS - 1)];
+                    for (int a1 = 0; a1 < 16; a1++) {
+                        const float4 u = row[r_unit(a1, lane)];
+                        v0[lane][a1] = make_float2(u.x, u.y);
+                        v1[lane][a1] = make_float2(u.z, u.w);
+                    }
+                    r_dif16_twiddle(v0[lane], v1[lane], tw);
+                }
+                for (int lane = 0; lane < 32; lane++)
+                    for (int kb = 0; kb < 16; kb++) {
+                        const int br = bitrev<16>(kb);
+                        row[r_unit(kb, lane)] = make_float4(v0[lane][br].x, v0[lane][br].y, v1[lane][br].x, v1[lane][br].y);
+                    }
+                float2 t[32][C::A0], tq[32];
+                for (int lane = 0; lane < 32; lane++) {
+                    const int kb2 = lane >> 1, h2 = lane & 1;
+                    const int E2 = c * C::NB + h2 * C::HB;
+                    const int e_idx = SF == 11 ? (E2 ? 1 : 0) : (E2 >> 1);
+                    const float2 wb1 = a.tw[(warp + 16 * kb2) & (C::SPS - 1)];
+                    const float2 wbE = a.tw[(E2 * (warp + 16 * kb2)) & (C::SPS - 1)];
+                    float2 g[C::HB][C::A0];
+                    for (int a0 = 0; a0 < C::A0; a0++) {
+                        if (SF == 11) {
+                            for (int e = 0; e < 2; e++) {
+                                const float4 u = row[r_unit(kb2, a0 * 4 + 2 * h2 + e)];
+                                g[2 * e][a0] = make_float2(u.x, u.y);
+                                g[(2 * e + 1) % C::HB][a0] = make_float2(u.z, u.w);
+                            }
+                        } else {
+                            const float4 u = row[r_unit(kb2, a0 * 2 + h2)];
+                            g[0][a0] = make_float2(u.x, u.y);
+                            g[C::HB - 1][a0] = make_float2(u.z, u.w);
+                        }
+                    }
+                    tq[lane] = make_float2(0.f, 0.f);
+                    if (warp == 0 && kb2 == 0) tq[lane] = r_pass2_quirk<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx]);
+                    r_pass2_sum<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx], t[lane]);
+                }
+                for (int lane = 0; lane < 32; lane++) {          // lane-pair exchange -> this CTA's partial sum per bin
+                    const int kb2 = lane >> 1, h2 = lane & 1;
+                    for (int i = 0; i < C::A0 / 2; i++) {
+                        const int q2 = i + h2 * (C::A0 / 2);
+                        part[c][warp + 16 * kb2 + 256 * q2] = cadd(t[lane][q2], t[lane ^ 1][q2]);
+                    }
+                }
+                if (warp == 0) part[c][C::L] = cadd(tq[0], tq[1]);
+            }
+        }
+        unsigned long long best = 0ull;
+        for (int k = 0; k < C::L; k++) {
+            float2 f = part[0][k];
+            if (C::CL == 2) f = cadd(f, part[1][k]);
+            if (k == C::L / 2) {
+                float2 q = part[0][C::L];
+                if (C::CL == 2) q = cadd(q, part[1][C::L]);
+                f = cadd(f, q);
+            }
+            const unsigned long long key = pack_key(cnorm2(f), (uint32_t)k);
+            best = key > best ? key : best;
+        }
+        bins[s] = key_idx(best);
+        if (mags) mags[s] = sqrtf(key_mag2(best));
+    }
+    for (int c = 0; c < C::CL; c++) { delete[] slots[c]; delete[] part[c]; }
+    delete[] keys;
+}
+
+}  // namespace lb

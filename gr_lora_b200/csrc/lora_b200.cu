@@ -48,6 +48,20 @@ struct Tables {          // offsets (bytes) inside the device blob, see lora_b20
     size_t down, up, down_ifreq, up_ifreq, up_ifreq_v, tw, total;
 };
 
+// Scratch of one K1 launch in flight: the 64-bit argmax keys that the split kernels merge with atomicMax and the
+// L2-resident exchange image + flags of the team kernels.  A launch zeroes it on its stream first, so two launches that
+// share one K1Scratch must not overlap: slot 0 (lora_b200_demod_fft_dev) is ordered across user streams by `done`,
+// and every slot of the host pipeline (lora_b200_demod_fft_host) owns its own.
+struct K1Scratch {
+    unsigned long long *packed = nullptr;
+    size_t packed_cap = 0;
+    void *xs = nullptr;
+    size_t xs_cap = 0;
+    cudaEvent_t done = nullptr;
+    cudaStream_t last = nullptr;
+    bool used = false;
+};
+
 }  // namespace
 
 struct lora_b200_decoder {
@@ -62,10 +76,7 @@ struct lora_b200_decoder {
     std::vector<uint8_t> h_tables;
     float down_ifreq_avg = 0.f, down_ifreq_sd = 0.f;
     // K1
-    unsigned long long *d_packed = nullptr;
-    size_t packed_cap = 0;
-    void *d_xs = nullptr;                 // k1_xchg: exchange scratch + flags
-    size_t xs_cap = 0;
+    K1Scratch k1s[3];                     // [0] device entry point, [1], [2] host pipeline slots
     float *d_k2_scratch = nullptr;
     int k2_grid = 0;
     // e2e host path
@@ -168,7 +179,7 @@ const T *tab(const lora_b200_decoder *d, size_t off) { return (const T *)(d->d_t
 
 // ---- K1 launch -----------------------------------------------------------------------------
 template <int SF>
-int launch_k1(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     using C = K1Cfg<SF>;
     static bool attr_set[64] = {};
     const size_t smem = sizeof(float2) * C::SMEM_ELEMS;
@@ -180,18 +191,18 @@ int launch_k1(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t
     const size_t n_work = ((n_symbols + C::G - 1) / C::G) * C::S;
     const int grid = (int)std::min<size_t>(n_work, (size_t)d->n_sms * 2);
     if (C::S > 1) {
-        if (d->packed_cap < n_symbols) {
-            if (d->d_packed) cudaFree(d->d_packed);
-            d->d_packed = nullptr; d->packed_cap = 0;
-            CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
-            d->packed_cap = n_symbols;
+        if (ks.packed_cap < n_symbols) {
+            if (ks.packed) cudaFree(ks.packed);
+            ks.packed = nullptr; ks.packed_cap = 0;
+            CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
+            ks.packed_cap = n_symbols;
         }
-        CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+        CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
     }
-    k1_fft_kernel<SF><<<grid, K1_THREADS, smem, st>>>(a, bins, mags, d->d_packed);
+    k1_fft_kernel<SF><<<grid, K1_THREADS, smem, st>>>(a, bins, mags, ks.packed);
     d->launches++;
     if (C::S > 1) {
-        k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+        k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
         d->launches++;
     }
     CU(cudaGetLastError());
@@ -200,7 +211,7 @@ int launch_k1(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t
 
 // SF7: one warp per symbol, TMA-fed shared-memory ring (k1_warp.cuh)
 template <int NWARPS, int NSLOT>
-int launch_k1_warp7(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1_warp7(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     static bool attr_set[64] = {};
     const size_t smem = sizeof(W7Smem<NWARPS, NSLOT>);
     if (!attr_set[d->device & 63]) {
@@ -217,7 +228,7 @@ int launch_k1_warp7(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, ui
 
 // SF8/SF9 (and SF7 as a cross-check): a group of 2^(SF-7) warps per symbol (k1_group.cuh)
 template <int SF, int NGROUPS, int NSLOT>
-int launch_k1_group(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1_group(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     static bool attr_set[64] = {};
     const size_t smem = sizeof(GSmem<SF, NGROUPS, NSLOT>);
     if (!attr_set[d->device & 63]) {
@@ -234,7 +245,7 @@ int launch_k1_group(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, ui
 
 // SF11/SF12: one cluster of 2/4 CTAs per symbol, pass 0 scattered over DSMEM (k1_cluster.cuh)
 template <int SF>
-int launch_k1_cluster(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1_cluster(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     using C = K1Cfg<SF>;
     using K = KCfg<SF>;
     static bool attr_set[64] = {};
@@ -243,13 +254,13 @@ int launch_k1_cluster(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, 
         CU(cudaFuncSetAttribute(k1_cluster_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[d->device & 63] = true;
     }
-    if (d->packed_cap < n_symbols) {
-        if (d->d_packed) cudaFree(d->d_packed);
-        d->d_packed = nullptr; d->packed_cap = 0;
-        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
-        d->packed_cap = n_symbols;
+    if (ks.packed_cap < n_symbols) {
+        if (ks.packed) cudaFree(ks.packed);
+        ks.packed = nullptr; ks.packed_cap = 0;
+        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
+        ks.packed_cap = n_symbols;
     }
-    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
     K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
     size_t n_clusters = std::min<size_t>(n_symbols, (size_t)(d->n_sms * 2) / K::CL);
     cudaLaunchConfig_t cfg = {};
@@ -264,16 +275,16 @@ int launch_k1_cluster(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, k1_cluster_kernel<SF>, a, d->d_packed));
+    CU(cudaLaunchKernelEx(&cfg, k1_cluster_kernel<SF>, a, ks.packed));
     d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
     d->launches++;
     CU(cudaGetLastError());
     return LORA_B200_OK;
 }
 
 // SF10: one 256-thread group per symbol, two radix-32 passes (k1_sf10.cuh)
-int launch_k1_sf10(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1_sf10(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     static bool attr_set[64] = {};
     const size_t smem = sizeof(S10Smem<2>);
     if (!attr_set[d->device & 63]) {
@@ -290,7 +301,7 @@ int launch_k1_sf10(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uin
 
 // SF11/SF12: cluster of 2/4 TMA-fed groups per symbol (k1_big.cuh)
 template <int SF>
-int launch_k1_big(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1_big(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     using B = BCfg<SF>;
     static bool attr_set[64] = {};
     const size_t smem = sizeof(BSmem<2>);
@@ -298,13 +309,13 @@ int launch_k1_big(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint
         CU(cudaFuncSetAttribute(k1_big_kernel<SF, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[d->device & 63] = true;
     }
-    if (d->packed_cap < n_symbols) {
-        if (d->d_packed) cudaFree(d->d_packed);
-        d->d_packed = nullptr; d->packed_cap = 0;
-        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
-        d->packed_cap = n_symbols;
+    if (ks.packed_cap < n_symbols) {
+        if (ks.packed) cudaFree(ks.packed);
+        ks.packed = nullptr; ks.packed_cap = 0;
+        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
+        ks.packed_cap = n_symbols;
     }
-    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
     K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
     const size_t n_clusters = std::max<size_t>(1, std::min<size_t>(n_symbols, (size_t)d->n_sms / B::CL));
     cudaLaunchConfig_t cfg = {};
@@ -319,9 +330,9 @@ int launch_k1_big(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, k1_big_kernel<SF, 2>, a, d->d_packed));
+    CU(cudaLaunchKernelEx(&cfg, k1_big_kernel<SF, 2>, a, ks.packed));
     d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
     d->launches++;
     CU(cudaGetLastError());
     return LORA_B200_OK;
@@ -345,7 +356,7 @@ unsigned long long *xg_watchdog_dev() {
 // SF10/SF11/SF12: teams of CL sub-CTAs per symbol, pass-0 outputs exchanged through an L2-resident scratch with TMA
 // stores / loads and global flags; one 512-thread CTA (512 / TH sub-CTAs) per SM (k1_xchg.cuh)
 template <int SF, int TH>
-int launch_k1_xchg(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1_xchg(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     using X = XCfg<SF, TH>;
     constexpr int NH = 512 / TH;
     static int max_cta_teams[64] = {};
@@ -363,27 +374,41 @@ int launch_k1_xchg(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uin
     // a CTA-team = CL CTAs = NH teams; do not launch CTA-teams that would get no symbol
     const size_t n_ct = std::max<size_t>(1, std::min<size_t>((n_symbols + NH - 1) / NH, (size_t)max_cta_teams[d->device & 63]));
     const size_t n_teams = n_ct * NH;
-    if (d->packed_cap < n_symbols) {
-        if (d->d_packed) cudaFree(d->d_packed);
-        d->d_packed = nullptr; d->packed_cap = 0;
-        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
-        d->packed_cap = n_symbols;
+    if (ks.packed_cap < n_symbols) {
+        if (ks.packed) cudaFree(ks.packed);
+        ks.packed = nullptr; ks.packed_cap = 0;
+        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
+        ks.packed_cap = n_symbols;
     }
     const size_t xs_bytes = n_teams * XG_NB * ((size_t)X::SPS * sizeof(float2) + sizeof(uint32_t));
-    if (d->xs_cap < xs_bytes) {
-        if (d->d_xs) cudaFree(d->d_xs);
-        d->d_xs = nullptr; d->xs_cap = 0;
-        CU(cudaMalloc(&d->d_xs, xs_bytes));
-        d->xs_cap = xs_bytes;
+    if (ks.xs_cap < xs_bytes) {
+        if (ks.xs) cudaFree(ks.xs);
+        ks.xs = nullptr; ks.xs_cap = 0;
+        CU(cudaMalloc(&ks.xs, xs_bytes));
+        ks.xs_cap = xs_bytes;
     }
-    float2 *xs = reinterpret_cast<float2 *>(d->d_xs);
+    float2 *xs = reinterpret_cast<float2 *>(ks.xs);
     uint32_t *flags = reinterpret_cast<uint32_t *>(xs + n_teams * XG_NB * (size_t)X::SPS);
-    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
     CU(cudaMemsetAsync(flags, 0, n_teams * XG_NB * sizeof(uint32_t), st));
     K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    k1_xchg_kernel<SF, TH><<<(unsigned)(n_ct * X::CL), 512, smem, st>>>(a, xs, flags, d->d_packed, xg_watchdog_dev(), getenv("LORA_B200_XG_NOSYNC") ? 1 : 0);
+    // the ranks of a team spin on each other's flags: the launch is COOPERATIVE, so either the whole grid is co-resident
+    // or the launch fails with an error (two such kernels on different streams run one after the other, never half each)
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_ct * X::CL));
+        cfg.blockDim = dim3(512);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k1_xchg_kernel<SF, TH>, a, xs, flags, ks.packed, xg_watchdog_dev(), getenv("LORA_B200_XG_NOSYNC") ? 1 : 0));
+    }
     d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
     d->launches++;
     CU(cudaGetLastError());
     return LORA_B200_OK;
@@ -391,7 +416,7 @@ int launch_k1_xchg(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uin
 
 // SF10/SF11/SF12: producer / consumer roles in one persistent kernel, exchange in L2 (k1_ab.cuh)
 template <int SF>
-int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+int launch_k1_ab(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     using A = ACfg<SF>;
     static int n_a_ctas[64] = {};
     const size_t smem = sizeof(ABSmem);
@@ -419,29 +444,41 @@ int launch_k1_ab(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint3
     // (tests/test_exchange_protocols.py models the protocol and shows both the bound and what happens below it)
     const uint32_t ring_min = 2u * (32u / A::R) * (3u * na / 8u) + 1u;
     if (ring < ring_min) ring = ring_min;
-    if (d->packed_cap < n_symbols) {
-        if (d->d_packed) cudaFree(d->d_packed);
-        d->d_packed = nullptr; d->packed_cap = 0;
-        CU(cudaMalloc(&d->d_packed, sizeof(unsigned long long) * n_symbols));
-        d->packed_cap = n_symbols;
+    if (ks.packed_cap < n_symbols) {
+        if (ks.packed) cudaFree(ks.packed);
+        ks.packed = nullptr; ks.packed_cap = 0;
+        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
+        ks.packed_cap = n_symbols;
     }
     const size_t xs_bytes = (size_t)ring * A::SPS * sizeof(float2) + 2 * (size_t)ring * AB_FSTRIDE * sizeof(uint32_t);
-    if (d->xs_cap < xs_bytes) {
-        if (d->d_xs) cudaFree(d->d_xs);
-        d->d_xs = nullptr; d->xs_cap = 0;
-        CU(cudaMalloc(&d->d_xs, xs_bytes));
-        d->xs_cap = xs_bytes;
+    if (ks.xs_cap < xs_bytes) {
+        if (ks.xs) cudaFree(ks.xs);
+        ks.xs = nullptr; ks.xs_cap = 0;
+        CU(cudaMalloc(&ks.xs, xs_bytes));
+        ks.xs_cap = xs_bytes;
     }
-    float2 *scratch = reinterpret_cast<float2 *>(d->d_xs);
+    float2 *scratch = reinterpret_cast<float2 *>(ks.xs);
     uint32_t *ready = reinterpret_cast<uint32_t *>(scratch + (size_t)ring * A::SPS), *done = ready + (size_t)ring * AB_FSTRIDE;
-    CU(cudaMemsetAsync(d->d_packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
     CU(cudaMemsetAsync(ready, 0, 2 * (size_t)ring * AB_FSTRIDE * sizeof(uint32_t), st));
     K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
     static const char *pv = getenv("LORA_B200_K1_AB_PROD");          // 2 = group producers (TMA in, in place, TMA out)
-    k1_ab_kernel<SF><<<na + nb, AB_WARPS * 32, smem, st>>>(a, scratch, ready, done, ring, nb, d->d_packed, xg_watchdog_dev(),
-                                                         pv && atoi(pv) == 2 ? 2 : 1);
+    {   // producers and consumers wait for each other: cooperative launch (see launch_k1_xchg)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(na + nb);
+        cfg.blockDim = dim3(AB_WARPS * 32);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k1_ab_kernel<SF>, a, scratch, ready, done, ring, nb, ks.packed, xg_watchdog_dev(),
+                              pv && atoi(pv) == 2 ? 2 : 1));
+    }
     d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(d->d_packed, n_symbols, bins, mags);
+    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
     d->launches++;
     CU(cudaGetLastError());
     return LORA_B200_OK;
@@ -466,74 +503,86 @@ int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 
     return v;
 }
 
-int dispatch_k1(lora_b200_decoder *d, const float2 *iq, size_t n, uint32_t *bins, float *mags, cudaStream_t st) {
+int dispatch_k1_impl(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n, uint32_t *bins, float *mags, cudaStream_t st) {
     if (!d->k1_ok) return fail(LORA_B200_EUNSUPPORTED, "FFT demodulator needs samp_rate/bandwidth == 8 and SF7..SF12");
     if (n == 0) return LORA_B200_OK;
     if (d->cfg.sf == 7) {
         switch (k1_variant()) {
-        case 1: return launch_k1_warp7<8, 3>(d, iq, n, bins, mags, st);
-        case 2: return launch_k1_warp7<12, 2>(d, iq, n, bins, mags, st);
-        case 3: return launch_k1_warp7<13, 2>(d, iq, n, bins, mags, st);
-        case 4: return launch_k1_warp7<9, 3>(d, iq, n, bins, mags, st);
-        case 5: return launch_k1_group<7, 12, 2>(d, iq, n, bins, mags, st);
-        case 6: return launch_k1_warp7<10, 2>(d, iq, n, bins, mags, st);
-        case 7: return launch_k1_warp7<11, 2>(d, iq, n, bins, mags, st);
+        case 1: return launch_k1_warp7<8, 3>(d, ks, iq, n, bins, mags, st);
+        case 2: return launch_k1_warp7<12, 2>(d, ks, iq, n, bins, mags, st);
+        case 3: return launch_k1_warp7<13, 2>(d, ks, iq, n, bins, mags, st);
+        case 4: return launch_k1_warp7<9, 3>(d, ks, iq, n, bins, mags, st);
+        case 5: return launch_k1_group<7, 12, 2>(d, ks, iq, n, bins, mags, st);
+        case 6: return launch_k1_warp7<10, 2>(d, ks, iq, n, bins, mags, st);
+        case 7: return launch_k1_warp7<11, 2>(d, ks, iq, n, bins, mags, st);
         default: break;
         }
     }
     if (k1_variant() != 0) {
         static const char *gv = getenv("LORA_B200_K1_GROUPS");        // tuning knob: "a" = fewer groups, deeper ring
         if (d->cfg.sf == 8) {
-            if (gv && gv[0] == 'a') return launch_k1_group<8, 4, 3>(d, iq, n, bins, mags, st);
-            if (gv && gv[0] == 'b') return launch_k1_group<8, 5, 2>(d, iq, n, bins, mags, st);
-            return launch_k1_group<8, 6, 2>(d, iq, n, bins, mags, st);
+            if (gv && gv[0] == 'a') return launch_k1_group<8, 4, 3>(d, ks, iq, n, bins, mags, st);
+            if (gv && gv[0] == 'b') return launch_k1_group<8, 5, 2>(d, ks, iq, n, bins, mags, st);
+            return launch_k1_group<8, 6, 2>(d, ks, iq, n, bins, mags, st);
         }
         if (d->cfg.sf == 9) {
-            if (gv && gv[0] == 'a') return launch_k1_group<9, 2, 3>(d, iq, n, bins, mags, st);
-            if (gv && gv[0] == 'b') return launch_k1_group<9, 2, 2>(d, iq, n, bins, mags, st);
-            return launch_k1_group<9, 3, 2>(d, iq, n, bins, mags, st);
+            if (gv && gv[0] == 'a') return launch_k1_group<9, 2, 3>(d, ks, iq, n, bins, mags, st);
+            if (gv && gv[0] == 'b') return launch_k1_group<9, 2, 2>(d, ks, iq, n, bins, mags, st);
+            return launch_k1_group<9, 3, 2>(d, ks, iq, n, bins, mags, st);
         }
         static const char *ab = getenv("LORA_B200_K1_AB");            // digits = SFs that use k1_ab ("012" = SF10,11,12)
         if (ab && d->cfg.sf >= 10 && strchr(ab, '0' + (d->cfg.sf - 10))) {
-            if (d->cfg.sf == 10) return launch_k1_ab<10>(d, iq, n, bins, mags, st);
-            if (d->cfg.sf == 11) return launch_k1_ab<11>(d, iq, n, bins, mags, st);
-            return launch_k1_ab<12>(d, iq, n, bins, mags, st);
+            if (d->cfg.sf == 10) return launch_k1_ab<10>(d, ks, iq, n, bins, mags, st);
+            if (d->cfg.sf == 11) return launch_k1_ab<11>(d, ks, iq, n, bins, mags, st);
+            return launch_k1_ab<12>(d, ks, iq, n, bins, mags, st);
         }
         static const char *xg = getenv("LORA_B200_K1_XCHG");          // digits = SFs that use k1_xchg ("012" = SF10,11,12)
         if (xg && d->cfg.sf >= 10 && strchr(xg, '0' + (d->cfg.sf - 10))) {
             static const char *xt = getenv("LORA_B200_K1_XCHG_T");    // "128": 128-thread CTAs, clusters of 4/8/16
             if (xt && atoi(xt) == 128) {
-                if (d->cfg.sf == 10) return launch_k1_xchg<10, 128>(d, iq, n, bins, mags, st);
-                if (d->cfg.sf == 11) return launch_k1_xchg<11, 128>(d, iq, n, bins, mags, st);
-                return launch_k1_xchg<12, 128>(d, iq, n, bins, mags, st);
+                if (d->cfg.sf == 10) return launch_k1_xchg<10, 128>(d, ks, iq, n, bins, mags, st);
+                if (d->cfg.sf == 11) return launch_k1_xchg<11, 128>(d, ks, iq, n, bins, mags, st);
+                return launch_k1_xchg<12, 128>(d, ks, iq, n, bins, mags, st);
             }
-            if (d->cfg.sf == 10) return launch_k1_xchg<10, 256>(d, iq, n, bins, mags, st);
-            if (d->cfg.sf == 11) return launch_k1_xchg<11, 256>(d, iq, n, bins, mags, st);
-            return launch_k1_xchg<12, 256>(d, iq, n, bins, mags, st);
+            if (d->cfg.sf == 10) return launch_k1_xchg<10, 256>(d, ks, iq, n, bins, mags, st);
+            if (d->cfg.sf == 11) return launch_k1_xchg<11, 256>(d, ks, iq, n, bins, mags, st);
+            return launch_k1_xchg<12, 256>(d, ks, iq, n, bins, mags, st);
         }
-        if (d->cfg.sf == 10 && !getenv("LORA_B200_K1_SF10_GENERIC")) return launch_k1_sf10(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 10 && !getenv("LORA_B200_K1_SF10_GENERIC")) return launch_k1_sf10(d, ks, iq, n, bins, mags, st);
         // k1_big (cluster of TMA-fed groups) measured 0.287 (SF11) / 0.130 (SF12): membar + lg_throttle stalls
         // around the two cluster barriers (profiles/r1_k1_big_sf11.md); the simpler kernels below are faster
         // today, so it stays opt-in until its exchange is made asynchronous (st.async + mbarrier).
         if (getenv("LORA_B200_K1_BIG")) {
-            if (d->cfg.sf == 11) return launch_k1_big<11>(d, iq, n, bins, mags, st);
-            if (d->cfg.sf == 12) return launch_k1_big<12>(d, iq, n, bins, mags, st);
+            if (d->cfg.sf == 11) return launch_k1_big<11>(d, ks, iq, n, bins, mags, st);
+            if (d->cfg.sf == 12) return launch_k1_big<12>(d, ks, iq, n, bins, mags, st);
         }
-        if (d->cfg.sf == 11) return launch_k1_cluster<11>(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 11) return launch_k1_cluster<11>(d, ks, iq, n, bins, mags, st);
         // SF12: the 4-CTA cluster version measured slower (0.107) than the DIF-split version (0.146); the team kernel
         // (k1_xchg.cuh, exchange through L2) measures 0.23 and is the default
-        if (d->cfg.sf == 12 && getenv("LORA_B200_K1_SF12_CLUSTER")) return launch_k1_cluster<12>(d, iq, n, bins, mags, st);
-        if (d->cfg.sf == 12 && !getenv("LORA_B200_K1_SF12_GENERIC")) return launch_k1_xchg<12, 256>(d, iq, n, bins, mags, st);
+        if (d->cfg.sf == 12 && getenv("LORA_B200_K1_SF12_CLUSTER")) return launch_k1_cluster<12>(d, ks, iq, n, bins, mags, st);
+        if (d->cfg.sf == 12 && !getenv("LORA_B200_K1_SF12_GENERIC")) return launch_k1_xchg<12, 256>(d, ks, iq, n, bins, mags, st);
     }
     switch (d->cfg.sf) {
-    case 7: return launch_k1<7>(d, iq, n, bins, mags, st);
-    case 8: return launch_k1<8>(d, iq, n, bins, mags, st);
-    case 9: return launch_k1<9>(d, iq, n, bins, mags, st);
-    case 10: return launch_k1<10>(d, iq, n, bins, mags, st);
-    case 11: return launch_k1<11>(d, iq, n, bins, mags, st);
-    case 12: return launch_k1<12>(d, iq, n, bins, mags, st);
+    case 7: return launch_k1<7>(d, ks, iq, n, bins, mags, st);
+    case 8: return launch_k1<8>(d, ks, iq, n, bins, mags, st);
+    case 9: return launch_k1<9>(d, ks, iq, n, bins, mags, st);
+    case 10: return launch_k1<10>(d, ks, iq, n, bins, mags, st);
+    case 11: return launch_k1<11>(d, ks, iq, n, bins, mags, st);
+    case 12: return launch_k1<12>(d, ks, iq, n, bins, mags, st);
     }
     return fail(LORA_B200_EUNSUPPORTED, "unsupported SF %u", d->cfg.sf);
+}
+
+// K1 on stream `st` with scratch `ks`: a launch that follows one on ANOTHER stream with the same scratch waits for it
+// (the memset of the keys / flags at the head of a launch must not run under the previous kernel)
+int dispatch_k1(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n, uint32_t *bins, float *mags, cudaStream_t st) {
+    if (!ks.done) CU(cudaEventCreateWithFlags(&ks.done, cudaEventDisableTiming));
+    if (ks.used && ks.last != st) CU(cudaStreamWaitEvent(st, ks.done, 0));
+    const int rc = dispatch_k1_impl(d, ks, iq, n, bins, mags, st);
+    if (rc) return rc;
+    CU(cudaEventRecord(ks.done, st));
+    ks.last = st; ks.used = true;
+    return LORA_B200_OK;
 }
 
 // ---- stream-path launch -----------------------------------------------------------------------
@@ -658,6 +707,10 @@ lora_b200_decoder *lora_b200_create(const lora_b200_config *cfg) {
         return nullptr;
     }
     if (cfg->n_streams == 0) { fail(LORA_B200_EINVAL, "n_streams must be >= 1"); return nullptr; }
+    if (cfg->cr > 4) {     // the reference would abort in deinterleave ("More than 8 bits per word", decoder_impl.cc:541-545)
+        fail(LORA_B200_EINVAL, "coding rate must be 0..4 (4/4 .. 4/8), got %u", cfg->cr);
+        return nullptr;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         fail(LORA_B200_ECUDA, "no CUDA device: liblora_b200 has no CPU fallback");
@@ -746,7 +799,11 @@ void lora_b200_destroy(lora_b200_decoder *d) {
     if (!d) return;
     cudaSetDevice(d->device);
     cudaDeviceSynchronize();
-    cudaFree(d->d_tables); cudaFree(d->d_packed); cudaFree(d->d_xs); cudaFree(d->d_k2_scratch);
+    cudaFree(d->d_tables); cudaFree(d->d_k2_scratch);
+    for (auto &ks : d->k1s) {
+        cudaFree(ks.packed); cudaFree(ks.xs);
+        if (ks.done) cudaEventDestroy(ks.done);
+    }
     for (int i = 0; i < 2; i++) {
         if (d->copy_streams[i]) cudaStreamDestroy(d->copy_streams[i]);
         cudaFree(d->d_chunk[i]); cudaFree(d->d_chunk_bins[i]); cudaFree(d->d_chunk_mags[i]);
@@ -832,7 +889,7 @@ int lora_b200_demod_fft_dev(lora_b200_decoder *d, const void *iq, size_t n_symbo
     if (!d || (!iq && n_symbols) || (!bins && n_symbols)) return fail(LORA_B200_EINVAL, "null argument");
     if (((uintptr_t)iq & 15u) != 0) return fail(LORA_B200_EINVAL, "iq must be 16-byte aligned");
     CU(cudaSetDevice(d->device));
-    return dispatch_k1(d, (const float2 *)iq, n_symbols, bins, mags, (cudaStream_t)stream);
+    return dispatch_k1(d, d->k1s[0], (const float2 *)iq, n_symbols, bins, mags, (cudaStream_t)stream);
 }
 
 int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, float *mags) {
@@ -865,7 +922,7 @@ int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symb
         const void *h = src + done * sym_bytes;
         if (!pinned) { memcpy(d->h_chunk[b], h, n * sym_bytes); h = d->h_chunk[b]; }
         CU(cudaMemcpyAsync(d->d_chunk[b], h, n * sym_bytes, cudaMemcpyHostToDevice, st));
-        int rc = dispatch_k1(d, (const float2 *)d->d_chunk[b], n, d->d_chunk_bins[b], d->d_chunk_mags[b], st);
+        int rc = dispatch_k1(d, d->k1s[1 + b], (const float2 *)d->d_chunk[b], n, d->d_chunk_bins[b], d->d_chunk_mags[b], st);
         if (rc) return rc;
         CU(cudaMemcpyAsync(bins + done, d->d_chunk_bins[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         if (mags) CU(cudaMemcpyAsync(mags + done, d->d_chunk_mags[b], n * sizeof(float), cudaMemcpyDeviceToHost, st));

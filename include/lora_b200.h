@@ -60,7 +60,7 @@ typedef struct lora_b200_config {
     uint32_t n_streams;          /* independent (channel, SF) streams sharing this config; >=1 */
     int32_t  device;             /* CUDA device ordinal; -1 = current device                   */
     uint32_t max_items_per_call; /* capacity of the per-stream staging buffer (0 = 1<<20)      */
-    uint32_t max_frames_per_call;/* per stream (0 = 64)                                        */
+    uint32_t max_frames_per_call;/* per stream (0 = 8)                                         */
     uint32_t trace_capacity;     /* per-stream lora_b200_step records kept per call (0 = none) */
 } lora_b200_config;
 

@@ -64,3 +64,18 @@ def test_product_does_not_import_oracle():
             if re.search(r"^\s*(from|import)\s+oracle\b|lora_oracle|liblora_oracle|oracle/", txt, re.M):
                 bad.append(str(p))
     assert not bad, bad
+
+
+def test_coding_rate_above_4_is_rejected():
+    """The reference aborts in deinterleave for more than 8 bits per word (lib/decoder_impl.cc:541-545); the library
+    refuses the configuration up front (device-independent check) instead of overrunning its words array."""
+    for cr in (5, 6, 7):
+        with pytest.raises(RuntimeError, match="coding rate must be 0..4"):
+            gr_lora_b200.decoder(1e6, 125000, 7, True, cr, True)
+
+
+def test_documented_defaults_match_the_implementation():
+    hdr = (ROOT / "include" / "lora_b200.h").read_text()
+    src = (ROOT / "gr_lora_b200" / "csrc" / "lora_b200.cu").read_text()
+    assert "max_frames_per_call;/* per stream (0 = 8)" in hdr
+    assert "if (d->cfg.max_frames_per_call == 0) d->cfg.max_frames_per_call = 8;" in src
