@@ -3,6 +3,7 @@ loaded the import fails loudly."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 from . import build as _build
 
@@ -49,11 +50,13 @@ SIGNATURES = {
     "lora_b200_tables_commit": (_i, [_vp]),
     "lora_b200_demod_fft_dev": (_i, [_vp, _vp, _sz, _vp, _vp, _vp]),
     "lora_b200_demod_fft_host": (_i, [_vp, _vp, _sz, _vp, _vp]),
+    "lora_b200_demod_fft_host_sc16": (_i, [_vp, _vp, C.c_float, _sz, _vp, _vp]),
     "lora_b200_demod_gradient_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "lora_b200_decode_codewords_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "lora_b200_deinterleave_dev": (_i, [_vp, _vp, _u32, _u32, _sz, _vp, _vp]),
     "lora_b200_work": (_i, [_vp, _u32, _vp, _sz, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_work_batch": (_i, [_vp, _vp, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
+    "lora_b200_work_batch_sc16": (_i, [_vp, _vp, C.c_float, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_stream_state": (_i, [_vp, _u32]),
     "lora_b200_stdout_last": (_i, [_vp, _u32, C.c_char_p, _sz]),
     "lora_b200_trace_read": (_i, [_vp, _u32, C.POINTER(Step), _sz, C.POINTER(_sz)]),
@@ -83,6 +86,9 @@ def lib() -> C.CDLL:
             if not _build.LIB.exists():
                 raise ImportError(f"liblora_b200.so is missing and could not be built: {exc}") from exc
             path = _build.LIB
+        alt = os.environ.get("LORA_B200_LIB")      # A/B runs of an alternative build of the same sources (tools/k1_ab.py)
+        if alt:
+            path = alt
         L = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)       # AttributeError here = ABI mismatch: fail loudly

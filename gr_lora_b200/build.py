@@ -37,13 +37,35 @@ def _sources():
     return sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + [ROOT / "include" / "lora_b200.h"]
 
 
+TRANSLATION_UNITS = ("lora_b200.cu", "k1_rows.cu", "channelizer.cu")
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    if force or _stale(LIB, _sources()):
-        flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-        cmd = [_nvcc(), *flags, "-o", str(LIB), str(CSRC / "lora_b200.cu"), str(CSRC / "channelizer.cu")]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.run(cmd, check=True)
+    """Every translation unit is compiled to build/obj/*.o (in parallel, only when stale) and linked into the .so."""
+    srcs = _sources()
+    if not (force or _stale(LIB, srcs)):
+        return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = ROOT / "build" / "obj"
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f not in ("-shared",) and not f.startswith("--use_fast_math")]
+    headers = [p for p in srcs if p.suffix != ".cu"]
+
+    def compile_one(name):
+        obj = obj_dir / (name + ".o")
+        if force or _stale(obj, [CSRC / name, *headers]):
+            cmd = [_nvcc(), *cflags, "-c", "-o", str(obj), str(CSRC / name)]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.run(cmd, check=True)
+        return obj
+
+    with ThreadPoolExecutor(len(TRANSLATION_UNITS)) as ex:
+        objs = list(ex.map(compile_one, TRANSLATION_UNITS))
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True)
     return LIB
 
 

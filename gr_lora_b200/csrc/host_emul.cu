@@ -9,6 +9,7 @@
 #include "k1_big.cuh"
 #include "k1_xchg.cuh"
 #include "k1_ab.cuh"
+#include "k1_rows.cuh"
 #include "int_chain.cuh"
 
 extern "C" {
@@ -45,6 +46,14 @@ int lb_k1_emulate_group(int sf, const float2 *x, size_t n_symbols, const float2 
     case 12: lb::kc_emulate<12>(a, bins, mags); break;
     default: return -1;
     }
+    return 0;
+}
+
+int lb_k1_emulate_rows(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
+    lb::K1Args a{x, chirp, tw, n_symbols};
+    if (sf == 11) lb::r_emulate<11>(a, bins, mags);
+    else if (sf == 12) lb::r_emulate<12>(a, bins, mags);
+    else return -1;
     return 0;
 }
 

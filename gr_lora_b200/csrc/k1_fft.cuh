@@ -290,7 +290,7 @@ k1_fft_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags,
     }
 }
 
-__global__ void k1_finalize_kernel(const unsigned long long *__restrict__ packed, size_t n,
+static __global__ void k1_finalize_kernel(const unsigned long long *__restrict__ packed, size_t n,
                                    uint32_t *__restrict__ bins, float *__restrict__ mags) {
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i < n) {

@@ -35,6 +35,9 @@
 // non-GPU tests, with shared memory, tensor memory and the peer exchange modelled as plain arrays).
 #pragma once
 #include "k1_warp.cuh"
+#ifdef __CUDACC__
+#include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+#endif
 
 namespace lb {
 
@@ -48,7 +51,7 @@ struct RCfg {
     static constexpr int CPA = NB / 2;                   // 16-byte units (branch pairs) per n1: 4 / 2
     static constexpr int ROW_F4 = A * CPA;               // 512 float4 = 8 KiB
     static constexpr uint32_t ROW_BYTES = 8192u;
-    static constexpr int NSLOT = SF == 12 ? 26 : 28;     // slot pool (SF12 gives 16 KiB to the peer-exchange buffer)
+    static constexpr int NSLOT = SF == 12 ? 24 : 28;     // slot pool, a multiple of 4 rows (SF12 gives 16 KiB to the peer-exchange buffer)
     static constexpr int T = 512, NW = 16;
     static constexpr int HB = NB / 2;                    // branches per lane in pass 2: 4 / 2
     static_assert(SF == 11 || SF == 12, "rows kernel: SF11, SF12");
@@ -72,7 +75,12 @@ template <int SF> LB_HD int r_sample(int rank, int warp, int lane, int j) {
     const int a = warp * C::A0 + r_a0<SF>(lane);
     return 8 * (j * C::A + a) + rank * C::NB + 2 * r_p<SF>(lane);
 }
-LB_HD int r_unit(int block, int within) { return block * 32 + (within ^ (block & 7)); }   // swizzled float4 index in a row
+// Swizzle of the 16-byte units inside a 512-byte block.  128-bit shared-memory accesses are served a quarter warp (8 lanes)
+// at a time; in pass 2 those 8 lanes are 4 consecutive blocks x the lane pair h, and h toggles unit bit 1 (SF11) / bit 0
+// (SF12), so the block number must toggle the other two of the low three bits.  (The first version XORed block & 7: two
+// lanes of every quarter met in one bank group, ncu: 2x the ideal wavefronts on the pass-2 loads.)
+template <int SF> LB_HD int r_swz(int block) { return SF == 11 ? ((block & 1) | ((block & 2) << 1)) : ((block & 3) << 1); }
+template <int SF> LB_HD int r_unit(int block, int within) { return block * 32 + (within ^ r_swz<SF>(block)); }   // float4 index in a row
 template <int SF> LB_HD int r_signed_bin(int k) { return k < RCfg<SF>::L / 2 ? k : k - RCfg<SF>::L; }
 // exponent (mod sps) of the per-q2 factor of W_sps^{e k'}: k' = kc + 16 kb + 256 q2 - (q2 >= A0/2 ? L : 0)
 template <int SF> LB_HD int r_cq_exp(int e, int q2) {
@@ -93,9 +101,11 @@ inline void r_build_consts(const float2 *tw_host, RConsts &c) {
 
 // ---- pass 0 / pass 1 arithmetic on registers -----------------------------------------------------------------------------
 // v0 / v1: the two branches of the thread's float4 column, 16 points each; tw[kc - 1] the output twiddles
-LB_HD void r_dif16_twiddle(float2 *v0, float2 *v1, const float2 *tw) {
+LB_HD void r_dif16(float2 *v0, float2 *v1) {
     dft_dif<16>(v0);
     dft_dif<16>(v1);
+}
+LB_HD void r_twiddle16(float2 *v0, float2 *v1, const float2 *tw) {
 #pragma unroll
     for (int k = 1; k < 16; k++) {
         const int br = bitrev<16>(k);
@@ -105,24 +115,24 @@ LB_HD void r_dif16_twiddle(float2 *v0, float2 *v1, const float2 *tw) {
 }
 
 // ---- pass 2 arithmetic ----------------------------------------------------------------------------------------------------
-// g[b][.]: A0 points of local branch (HB h + b); after the DFT g[b][bitrev(q2)] = G_r[kc + 16 kb + 256 q2].
-// Returns in t[q2] this lane's share of the sum over the branches, already multiplied by the power of w that places
-// it:  t[q2] = w^{E} * sum_b w^b g[b][q2],  E = global index of the lane's first branch,  w = W_sps^{k'(q2)}.
+// g[b][.]: A0 points of local branch (HB h + b); after r_pass2_dft g[b][bitrev(q2)] = G_r[kc + 16 kb + 256 q2].
+// r_pass2_term returns this lane's share t(q2) of the sum over the branches, already multiplied by the power of w that places
+// it:  t(q2) = w^{E} * sum_b w^b g[b][q2],  E = global index of the lane's first branch,  w = W_sps^{k'(q2)}.
 // wb1 = W_sps^{kc + 16 kb}, wbE = W_sps^{E (kc + 16 kb)};  cq1 / cqE the per-q2 factors (RConsts rows).
 template <int SF>
-LB_HD void r_pass2_sum(float2 (*g)[RCfg<SF>::A0], int E, float2 wb1, float2 wbE, const float2 *cq1, const float2 *cqE, float2 *t) {
+LB_HD void r_pass2_dft(float2 (*g)[RCfg<SF>::A0]) {
+#pragma unroll
+    for (int b = 0; b < RCfg<SF>::HB; b++) dft_dif<RCfg<SF>::A0>(g[b]);
+}
+template <int SF>
+LB_HD float2 r_pass2_term(float2 (*g)[RCfg<SF>::A0], int q2, int E, float2 wb1, float2 wbE, const float2 *cq1, const float2 *cqE) {
     using C = RCfg<SF>;
+    const int br = bitrev<C::A0>(q2);
+    const float2 w = cmul(wb1, cq1[q2]);
+    float2 acc = g[C::HB - 1][br];
 #pragma unroll
-    for (int b = 0; b < C::HB; b++) dft_dif<C::A0>(g[b]);
-#pragma unroll
-    for (int q2 = 0; q2 < C::A0; q2++) {
-        const int br = bitrev<C::A0>(q2);
-        const float2 w = cmul(wb1, cq1[q2]);
-        float2 acc = g[C::HB - 1][br];
-#pragma unroll
-        for (int b = C::HB - 2; b >= 0; b--) acc = cfma(acc, w, g[b][br]);
-        t[q2] = E ? cmul(acc, cmul(wbE, cqE[q2])) : acc;
-    }
+    for (int b = C::HB - 2; b >= 0; b--) acc = cfma(acc, w, g[b][br]);
+    return E ? cmul(acc, cmul(wbE, cqE[q2])) : acc;
 }
 // the second evaluation of bin N/2 (tmp[N/2] += F[N/2], :450): same G values, conjugate twiddles (W_sps^{+N/2 r})
 template <int SF>
@@ -160,6 +170,15 @@ LB_D void tm_ld16(uint32_t taddr, float2 *v) {
                  : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
                    "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
                  : "r"(taddr) : "memory");
+}
+
+LB_D float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+LB_D void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // ---- cluster helpers (SF12) -----------------------------------------------------------------------------------------------
@@ -206,15 +225,15 @@ struct RSmem {
     uint32_t tm_base;
 };
 
-struct RParams {
+struct alignas(64) RParams {
+    CUtensorMap tmap;                  // SF12: 2-D view of the IQ batch {16 floats per n1, n_symbols * L}, box {8, 256}
     K1Args a;
-    const void *tmap;                  // SF12: CUtensorMap of the IQ batch, in global memory
     unsigned long long *packed;        // SF12: per-symbol argmax keys merged by atomicMax (finalised by k1_finalize_kernel)
     uint32_t *bins;                    // SF11: written directly
     float *mags;
 };
 
-__device__ __constant__ RConsts r_consts_dev[2];          // [SF - 11]
+static __device__ __constant__ RConsts r_consts_dev[2];          // [SF - 11]
 
 template <int SF>
 __global__ void __launch_bounds__(RCfg<SF>::T, 1)
@@ -252,7 +271,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         float4 *dst = sm.slots[g % C::NSLOT];
         mbar_expect_tx(bar, C::ROW_BYTES);
         if (C::CL == 1) bulk_g2s(dst, a.x + sym * C::SPS + (size_t)j * (C::SPS / 16), C::ROW_BYTES, bar);
-        else tma_rows_2d(dst, P.tmap, (int)(rank * 8u), (int)(sym * C::L + (size_t)j * C::A), bar);
+        else tma_rows_2d(dst, &P.tmap, (int)(rank * 8u), (int)(sym * C::L + (size_t)j * C::A), bar);
     };
     if (tid == 0)
         for (int g = 0; g < C::NSLOT; g++) issue_row((size_t)g);
@@ -303,9 +322,29 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
     if (C::CL == 2) cluster_sync_all(); else __syncthreads();     // tw1 columns of warps 0-3 are read by every warp; peers' barriers are initialised
     tm_fence_after();
 
-    for (size_t s = 0; s < n_mine; s++) {
-        const size_t sym = unit + s * n_units;
+    // ---- shared-memory addressing (32-bit shared addresses; every per-access term below is an immediate) -------------------
+    // rows of the current symbol sit in slots (base + j) mod NSLOT, base = 16 s mod NSLOT; NSLOT and 16 are multiples of 4, so
+    // the four rows of a group 4q .. 4q+3 are consecutive slots: one byte offset per group and symbol
+    const uint32_t slots0 = smem_u32(&sm.slots[0][0]);
+    const uint32_t ld0 = slots0 + (uint32_t)(warp * 32 + lane) * 16u;                     // pass-0 loads: natural order
+    const uint32_t st0 = slots0 + (uint32_t)r_unit<SF>(warp, lane) * 16u;                 // pass-0 stores: swizzled
+    uint32_t lane_sw[4];                                                                   // pass 1: (lane ^ swizzle) * 16, 4 swizzle values
+#pragma unroll
+    for (int c = 0; c < 4; c++) lane_sw[c] = (uint32_t)(lane ^ r_swz<SF>(c)) * 16u;
+    // pass 2: unit = K ^ m with K = (a0, e) a compile-time number and m = (the lane pair's bit) ^ swizzle(kb) a lane constant;
+    // only the low three unit bits meet m, so 4 XORed addresses per symbol cover all 16 loads
+    const uint32_t m2 = (uint32_t)((SF == 11 ? 2 * (lane & 1) : (lane & 1)) ^ r_swz<SF>(lane >> 1)) * 16u + (uint32_t)(lane >> 1) * 512u;
+    int base = 0;
+    for (size_t s = 0; s < n_mine; s++, base = base + 16 >= C::NSLOT ? base + 16 - C::NSLOT : base + 16) {
         const size_t g0 = s * 16;
+        uint32_t gb[4];
+        {
+            int t = base;
+#pragma unroll
+            for (int q = 0; q < 4; q++) { gb[q] = (uint32_t)t * C::ROW_BYTES; t += 4; if (t >= C::NSLOT) t -= C::NSLOT; }
+        }
+        uint32_t rowaddr;
+        { int t = base + warp; if (t >= C::NSLOT) t -= C::NSLOT; rowaddr = slots0 + (uint32_t)t * C::ROW_BYTES; }
         mbar_wait(&sm.sym_full[s % R_NSYM_BAR], (uint32_t)((s / R_NSYM_BAR) & 1));
 
         // ---- pass 0: radix 16 over the rows, warp = a1 block -----------------------------------------------------------
@@ -316,8 +355,9 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 float2 ch[8];
                 tm_ld16(tm_lane + (uint32_t)(R_TM_CHIRP + 64 * (warp >> 2) + 16 * q), ch);
                 float4 xv[4];
+                const uint32_t ga = ld0 + gb[q];
 #pragma unroll
-                for (int jj = 0; jj < 4; jj++) xv[jj] = sm.slots[(g0 + 4 * q + jj) % C::NSLOT][warp * 32 + lane];
+                for (int jj = 0; jj < 4; jj++) xv[jj] = lds128(ga + (uint32_t)jj * C::ROW_BYTES);
                 tm_wait_ld();
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) {
@@ -325,14 +365,15 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                     v1[4 * q + jj] = cmul(make_float2(xv[jj].z, xv[jj].w), ch[2 * jj + 1]);
                 }
             }
+            r_dif16(v0, v1);
             tm_ld16(tm_lane + (uint32_t)(R_TM_TW0 + 32 * (warp >> 2)), tw);
             tm_ld16(tm_lane + (uint32_t)(R_TM_TW0 + 32 * (warp >> 2) + 16), tw + 8);
             tm_wait_ld();
-            r_dif16_twiddle(v0, v1, tw);
+            r_twiddle16(v0, v1, tw);
 #pragma unroll
             for (int kc = 0; kc < 16; kc++) {
                 const int br = bitrev<16>(kc);
-                sm.slots[(g0 + kc) % C::NSLOT][r_unit(warp, lane)] = make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y);
+                sts128(st0 + gb[kc >> 2] + (uint32_t)(kc & 3) * C::ROW_BYTES, make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y));
             }
         }
         __syncthreads();
@@ -350,58 +391,86 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 else { P.bins[psym] = key_idx(k); if (P.mags) P.mags[psym] = sqrtf(key_mag2(k)); }
             }
         }
-        float4 *row = sm.slots[(g0 + warp) % C::NSLOT];
         // ---- pass 1: radix 16 over a1 inside row kc = warp -------------------------------------------------------------
         {
             float2 v0[16], v1[16], tw[16];
-            tm_ld16(sm.tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)R_TM_TW1, tw);
-            tm_ld16(sm.tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(R_TM_TW1 + 16), tw + 8);
+            uint32_t ra[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) ra[c] = rowaddr + lane_sw[c];
 #pragma unroll
             for (int a1 = 0; a1 < 16; a1++) {
-                const float4 u = row[r_unit(a1, lane)];
+                const float4 u = lds128(ra[a1 & 3] + (uint32_t)a1 * 512u);
                 v0[a1] = make_float2(u.x, u.y);
                 v1[a1] = make_float2(u.z, u.w);
             }
+            r_dif16(v0, v1);
+            tm_ld16(tm_lane + (uint32_t)R_TM_TW1, tw);
+            tm_ld16(tm_lane + (uint32_t)(R_TM_TW1 + 16), tw + 8);
             tm_wait_ld();
-            r_dif16_twiddle(v0, v1, tw);
+            r_twiddle16(v0, v1, tw);
 #pragma unroll
             for (int kb = 0; kb < 16; kb++) {
                 const int br = bitrev<16>(kb);
-                row[r_unit(kb, lane)] = make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y);
+                sts128(ra[kb & 3] + (uint32_t)kb * 512u, make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y));
             }
         }
         __syncwarp();
         // ---- pass 2: radix A0 over a0, branch sum, argmax ---------------------------------------------------------------
         unsigned long long best = 0ull;
         {
-            float2 g[C::HB][C::A0], t[C::A0];
-            if (SF == 11) {
+            float2 g[C::HB][C::A0];
+            {
+                const uint32_t qm = rowaddr + m2;
+                uint32_t pa[4];
+                if (SF == 11) {
+                    // K = a0 * 4 + e: unit bits 0 (e) and 2 (a0 & 1) meet m; (a0 >> 1) * 128 bytes stays an immediate
 #pragma unroll
-                for (int a0 = 0; a0 < C::A0; a0++)
+                    for (int c = 0; c < 4; c++) pa[c] = qm ^ (uint32_t)(((c >> 1) * 4 + (c & 1)) * 16);
 #pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const float4 u = row[r_unit(kb2, a0 * 4 + 2 * h2 + e)];
-                        g[2 * e][a0] = make_float2(u.x, u.y);
-                        g[(2 * e + 1) % C::HB][a0] = make_float2(u.z, u.w);
+                    for (int a0 = 0; a0 < C::A0; a0++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++) {
+                            const float4 u = lds128(pa[(a0 & 1) * 2 + e] + (uint32_t)(a0 >> 1) * 128u);
+                            g[2 * e][a0] = make_float2(u.x, u.y);
+                            g[(2 * e + 1) % C::HB][a0] = make_float2(u.z, u.w);
+                        }
+                } else {
+                    // K = a0 * 2: unit bits 1, 2 (a0 & 3) meet m; (a0 >> 2) * 128 bytes stays an immediate
+#pragma unroll
+                    for (int c = 0; c < 4; c++) pa[c] = qm ^ (uint32_t)(c * 2 * 16);
+#pragma unroll
+                    for (int a0 = 0; a0 < C::A0; a0++) {
+                        const float4 u = lds128(pa[a0 & 3] + (uint32_t)(a0 >> 2) * 128u);
+                        g[0][a0] = make_float2(u.x, u.y);
+                        g[C::HB - 1][a0] = make_float2(u.z, u.w);
                     }
-            } else {
-#pragma unroll
-                for (int a0 = 0; a0 < C::A0; a0++) {
-                    const float4 u = row[r_unit(kb2, a0 * 2 + h2)];
-                    g[0][a0] = make_float2(u.x, u.y);
-                    g[C::HB - 1][a0] = make_float2(u.z, u.w);
                 }
             }
+            r_pass2_dft<SF>(g);
+            // the row has been read (the DFT above consumed every loaded register of this lane, the warp barrier covers the
+            // others): re-arm its slot NOW, so that the TMA of the row that lands here NSLOT rows later runs under the rest
+            // of pass 2 -- the rows of the next symbol that wait for slots of this one are its last ones, and their
+            // latency would otherwise be exposed at the top of the loop (first capture: 15 % of all samples there)
+            __syncwarp();
+            if (lane == 0) {
+                fence_proxy_async();
+                issue_row(g0 + (size_t)warp + (size_t)C::NSLOT);
+            }
+            // the products of the lane's twiddle bases with the per-q2 constants are loop invariant; hoisted out of the
+            // symbol loop they would occupy (and spill) 64 registers, so the bases are made opaque here
+            float2 wb1s = wb1, wbEs = wbE;
+            asm volatile("" : "+f"(wb1s.x), "+f"(wb1s.y), "+f"(wbEs.x), "+f"(wbEs.y));
             const bool quirk_warp = warp == 0;                       // bin N/2 = (kc 0, kb 0, q2 A0/2): lanes 0 and 1 of warp 0
             float2 tq = make_float2(0.f, 0.f);
-            if (quirk_warp && kb2 == 0) tq = r_pass2_quirk<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx]);
-            r_pass2_sum<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx], t);
+            if (quirk_warp && kb2 == 0) tq = r_pass2_quirk<SF>(g, E2, wb1s, wbEs, rc.cq[0], rc.cq[e_idx]);
             // lane pair: h = 0 keeps q2 < A0/2, h = 1 keeps q2 >= A0/2; each sends the other half
             float2 f[C::A0 / 2];
 #pragma unroll
             for (int i = 0; i < C::A0 / 2; i++) {
-                const float2 give = h2 ? t[i] : t[i + C::A0 / 2];
-                const float2 keep = h2 ? t[i + C::A0 / 2] : t[i];
+                const float2 tlo = r_pass2_term<SF>(g, i, E2, wb1s, wbEs, rc.cq[0], rc.cq[e_idx]);
+                const float2 thi = r_pass2_term<SF>(g, i + C::A0 / 2, E2, wb1s, wbEs, rc.cq[0], rc.cq[e_idx]);
+                const float2 give = h2 ? tlo : thi;
+                const float2 keep = h2 ? thi : tlo;
                 float2 got;
                 got.x = __shfl_xor_sync(0xffffffffu, give.x, 1);
                 got.y = __shfl_xor_sync(0xffffffffu, give.y, 1);
@@ -463,12 +532,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
             const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
             best = o > best ? o : best;
         }
-        // every lane is done with the row (the shuffles above are the warp's convergence point): re-arm its slot
-        if (lane == 0) {
-            sm.keys[s & 1][warp] = best;
-            fence_proxy_async();
-            issue_row(g0 + (size_t)warp + (size_t)C::NSLOT);
-        }
+        if (lane == 0) sm.keys[s & 1][warp] = best;
     }
     __syncthreads();
     if (n_mine > 0 && warp == 0) {
@@ -529,12 +593,13 @@ inline void r_emulate(const K1Args &a, uint32_t *bins, float *mags) {
                         v0[lane][j] = cmul(make_float2(xv.x, xv.y), a.chirp[n]);
                         v1[lane][j] = cmul(make_float2(xv.z, xv.w), a.chirp[n + 1]);
                     }
-                    r_dif16_twiddle(v0[lane], v1[lane], tw);
+                    r_dif16(v0[lane], v1[lane]);
+                    r_twiddle16(v0[lane], v1[lane], tw);
                 }
                 for (int lane = 0; lane < 32; lane++)
                     for (int kc = 0; kc < 16; kc++) {
                         const int br = bitrev<16>(kc);
-                        slot(g0 + kc)[r_unit(warp, lane)] = make_float4(v0[lane][br].x, v0[lane][br].y, v1[lane][br].x, v1[lane][br].y);
+                        slot(g0 + kc)[r_unit<SF>(warp, lane)] = make_float4(v0[lane][br].x, v0[lane][br].y, v1[lane][br].x, v1[lane][br].y);
                     }
             }
             for (int warp = 0; warp < C::NW; warp++) {           // pass 1 + pass 2 of row kc = warp
@@ -544,16 +609,17 @@ inline void r_emulate(const K1Args &a, uint32_t *bins, float *mags) {
                     float2 tw[16];
                     for (int kb = 1; kb < 16; kb++) tw[kb - 1] = a.tw[(128 * r_a0<SF>(lane) * kb) & (C::SPS - 1)];
                     for (int a1 = 0; a1 < 16; a1++) {
-                        const float4 u = row[r_unit(a1, lane)];
+                        const float4 u = row[r_unit<SF>(a1, lane)];
                         v0[lane][a1] = make_float2(u.x, u.y);
                         v1[lane][a1] = make_float2(u.z, u.w);
                     }
-                    r_dif16_twiddle(v0[lane], v1[lane], tw);
+                    r_dif16(v0[lane], v1[lane]);
+                    r_twiddle16(v0[lane], v1[lane], tw);
                 }
                 for (int lane = 0; lane < 32; lane++)
                     for (int kb = 0; kb < 16; kb++) {
                         const int br = bitrev<16>(kb);
-                        row[r_unit(kb, lane)] = make_float4(v0[lane][br].x, v0[lane][br].y, v1[lane][br].x, v1[lane][br].y);
+                        row[r_unit<SF>(kb, lane)] = make_float4(v0[lane][br].x, v0[lane][br].y, v1[lane][br].x, v1[lane][br].y);
                     }
                 float2 t[32][C::A0], tq[32];
                 for (int lane = 0; lane < 32; lane++) {
@@ -566,19 +632,20 @@ inline void r_emulate(const K1Args &a, uint32_t *bins, float *mags) {
                     for (int a0 = 0; a0 < C::A0; a0++) {
                         if (SF == 11) {
                             for (int e = 0; e < 2; e++) {
-                                const float4 u = row[r_unit(kb2, a0 * 4 + 2 * h2 + e)];
+                                const float4 u = row[r_unit<SF>(kb2, a0 * 4 + 2 * h2 + e)];
                                 g[2 * e][a0] = make_float2(u.x, u.y);
                                 g[(2 * e + 1) % C::HB][a0] = make_float2(u.z, u.w);
                             }
                         } else {
-                            const float4 u = row[r_unit(kb2, a0 * 2 + h2)];
+                            const float4 u = row[r_unit<SF>(kb2, a0 * 2 + h2)];
                             g[0][a0] = make_float2(u.x, u.y);
                             g[C::HB - 1][a0] = make_float2(u.z, u.w);
                         }
                     }
                     tq[lane] = make_float2(0.f, 0.f);
+                    r_pass2_dft<SF>(g);
                     if (warp == 0 && kb2 == 0) tq[lane] = r_pass2_quirk<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx]);
-                    r_pass2_sum<SF>(g, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx], t[lane]);
+                    for (int q2 = 0; q2 < C::A0; q2++) t[lane][q2] = r_pass2_term<SF>(g, q2, E2, wb1, wbE, rc.cq[0], rc.cq[e_idx]);
                 }
                 for (int lane = 0; lane < 32; lane++) {          // lane-pair exchange -> this CTA's partial sum per bin
                     const int kb2 = lane >> 1, h2 = lane & 1;

@@ -12,6 +12,7 @@
 #include "k1_xchg.cuh"
 #include "k1_ab.cuh"
 #include "rx_stream.cuh"
+#include "k1_rows.h"
 
 #include <algorithm>
 #include <cmath>
@@ -82,6 +83,7 @@ struct lora_b200_decoder {
     // e2e host path
     cudaStream_t copy_streams[2] = {nullptr, nullptr};
     void *d_chunk[2] = {nullptr, nullptr};
+    void *d_chunk16[2] = {nullptr, nullptr};
     void *h_chunk[2] = {nullptr, nullptr};
     uint32_t *d_chunk_bins[2] = {nullptr, nullptr};
     float *d_chunk_mags[2] = {nullptr, nullptr};
@@ -98,6 +100,8 @@ struct lora_b200_decoder {
     lora_b200_step *d_trace = nullptr;
     uint32_t *d_trace_n = nullptr;
     float2 *d_stage = nullptr;            // [n_streams][max_items]
+    short2 *d_stage16 = nullptr;          // same shape, int16 I/Q ingest (lora_b200_work_batch_sc16)
+    std::vector<cudaEvent_t> stage_events;
     float2 *h_stage = nullptr;            // pinned, same shape
     size_t stage_cap = 0;                 // items
     std::vector<unsigned long long> h_consumed;
@@ -484,6 +488,31 @@ int launch_k1_ab(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n
     return LORA_B200_OK;
 }
 
+// SF11 / SF12: every sample stays inside one SM (k1_rows.cuh; SF12 = cluster of two CTAs per symbol); own translation unit
+int launch_k1_rows(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    const int sf = d->cfg.sf;
+    if (sf == 12) {
+        if (ks.packed_cap < n_symbols) {
+            if (ks.packed) cudaFree(ks.packed);
+            ks.packed = nullptr; ks.packed_cap = 0;
+            CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
+            ks.packed_cap = n_symbols;
+        }
+        CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
+    }
+    char err[256] = {0};
+    const int rc = k1_rows_launch(sf, d->device, d->n_sms, iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw),
+                                  (const float2 *)(d->h_tables.data() + d->toff.tw), n_symbols, bins, mags, ks.packed, st, err, sizeof err);
+    if (rc) return fail(LORA_B200_ECUDA, "k1_rows: %s", err);
+    d->launches++;
+    if (sf == 12) {
+        k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
+        d->launches++;
+        CU(cudaGetLastError());
+    }
+    return LORA_B200_OK;
+}
+
 int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
     static int v = -1;
     if (v < 0) {
@@ -530,6 +559,8 @@ int dispatch_k1_impl(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size
             if (gv && gv[0] == 'b') return launch_k1_group<9, 2, 2>(d, ks, iq, n, bins, mags, st);
             return launch_k1_group<9, 3, 2>(d, ks, iq, n, bins, mags, st);
         }
+        static const char *rows = getenv("LORA_B200_K1_ROWS");        // "0": the round-1 kernels for SF11 / SF12 (A/B runs)
+        if ((d->cfg.sf == 11 || d->cfg.sf == 12) && !(rows && rows[0] == '0')) return launch_k1_rows(d, ks, iq, n, bins, mags, st);
         static const char *ab = getenv("LORA_B200_K1_AB");            // digits = SFs that use k1_ab ("012" = SF10,11,12)
         if (ab && d->cfg.sf >= 10 && strchr(ab, '0' + (d->cfg.sf - 10))) {
             if (d->cfg.sf == 10) return launch_k1_ab<10>(d, ks, iq, n, bins, mags, st);
@@ -629,10 +660,13 @@ void append_hex(std::string &s, const uint8_t *v, size_t n, bool endline, bool a
     if (endline) s += "\n";
 }
 
-int run_rx(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t n_items, uint32_t stream_base,
-           uint32_t n_launch, size_t *consumed, lora_b200_frame_cb cb, void *user) {
-    cudaStream_t st = d->rx_stream;
-    CU(cudaMemsetAsync(d->d_n_frames, 0, sizeof(uint32_t), st));
+int rx_begin(lora_b200_decoder *d) {
+    CU(cudaMemsetAsync(d->d_n_frames, 0, sizeof(uint32_t), d->rx_stream));
+    return LORA_B200_OK;
+}
+
+// the state machine for streams [stream_base, stream_base + n_launch) over staged IQ (one CTA per stream), async on rx_stream
+int rx_launch(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t n_items, uint32_t stream_base, uint32_t n_launch) {
     RxParams p;
     memset(&p, 0, sizeof p);
     p.iq = d_iq; p.stride_items = stride_items; p.n_items = n_items; p.stream_base = stream_base;
@@ -648,8 +682,12 @@ int run_rx(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t
     p.frames = d->d_frames; p.n_frames = d->d_n_frames; p.frame_cap = d->frame_cap;
     p.max_frames_per_stream = d->cfg.max_frames_per_call;
     p.trace = d->d_trace; p.trace_cap = d->cfg.trace_capacity; p.trace_n = d->d_trace_n;
-    int rc = launch_rx(d, p, (int)n_launch, st);
-    if (rc) return rc;
+    return launch_rx(d, p, (int)n_launch, d->rx_stream);
+}
+
+// K8 on the queued frames, results back to the host, frames delivered per stream in sequence order
+int rx_finish(lora_b200_decoder *d, uint32_t stream_base, uint32_t n_launch, size_t *consumed, lora_b200_frame_cb cb, void *user) {
+    cudaStream_t st = d->rx_stream;
     const int k8_grid = (int)std::min<uint32_t>(d->frame_cap, (uint32_t)d->n_sms * 4u);
     k8_frames_kernel<<<k8_grid, 128, 0, st>>>(d->d_frames, d->d_n_frames, d->frame_cap, d->d_frames_out);
     d->launches++;
@@ -684,6 +722,31 @@ int run_rx(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t
         if (cb) cb(user, f.stream, f.bytes, f.len);
     }
     return LORA_B200_OK;
+}
+
+int run_rx(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t n_items, uint32_t stream_base,
+           uint32_t n_launch, size_t *consumed, lora_b200_frame_cb cb, void *user) {
+    int rc = rx_begin(d);
+    if (!rc) rc = rx_launch(d, d_iq, stride_items, n_items, stream_base, n_launch);
+    if (!rc) rc = rx_finish(d, stream_base, n_launch, consumed, cb, user);
+    return rc;
+}
+
+// SDR-native ingest: interleaved int16 I/Q -> gr_complex scaled by `scale` (what a host-side sc16 -> fc32 converter does)
+__global__ void sc16_to_cf32_kernel(const short2 *__restrict__ in, float2 *__restrict__ out, size_t n, float scale) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 4 <= n && (((uintptr_t)(in + i)) & 15u) == 0 && (((uintptr_t)(out + i)) & 15u) == 0) {
+            const int4 v = __ldcs(reinterpret_cast<const int4 *>(in + i));
+            const short2 s0 = *reinterpret_cast<const short2 *>(&v.x), s1 = *reinterpret_cast<const short2 *>(&v.y);
+            const short2 s2 = *reinterpret_cast<const short2 *>(&v.z), s3 = *reinterpret_cast<const short2 *>(&v.w);
+            float4 *o = reinterpret_cast<float4 *>(out + i);
+            o[0] = make_float4(s0.x * scale, s0.y * scale, s1.x * scale, s1.y * scale);
+            o[1] = make_float4(s2.x * scale, s2.y * scale, s3.x * scale, s3.y * scale);
+        } else {
+            for (size_t k = i; k < n && k < i + 4; k++) out[k] = make_float2(in[k].x * scale, in[k].y * scale);
+        }
+    }
 }
 
 }  // namespace
@@ -806,13 +869,14 @@ void lora_b200_destroy(lora_b200_decoder *d) {
     }
     for (int i = 0; i < 2; i++) {
         if (d->copy_streams[i]) cudaStreamDestroy(d->copy_streams[i]);
-        cudaFree(d->d_chunk[i]); cudaFree(d->d_chunk_bins[i]); cudaFree(d->d_chunk_mags[i]);
+        cudaFree(d->d_chunk[i]); cudaFree(d->d_chunk16[i]); cudaFree(d->d_chunk_bins[i]); cudaFree(d->d_chunk_mags[i]);
         if (d->h_chunk[i]) cudaFreeHost(d->h_chunk[i]);
     }
     if (d->rx_stream) cudaStreamDestroy(d->rx_stream);
     cudaFree(d->d_states); cudaFree(d->d_scratch); cudaFree(d->d_consumed); cudaFree(d->d_frames);
     cudaFree(d->d_frames_out); cudaFree(d->d_n_frames); cudaFree(d->d_trace); cudaFree(d->d_trace_n);
-    cudaFree(d->d_stage);
+    cudaFree(d->d_stage); cudaFree(d->d_stage16);
+    for (cudaEvent_t e : d->stage_events) if (e) cudaEventDestroy(e);
     if (d->h_stage) cudaFreeHost(d->h_stage);
     delete d;
 }
@@ -892,20 +956,25 @@ int lora_b200_demod_fft_dev(lora_b200_decoder *d, const void *iq, size_t n_symbo
     return dispatch_k1(d, d->k1s[0], (const float2 *)iq, n_symbols, bins, mags, (cudaStream_t)stream);
 }
 
-int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, float *mags) {
+// K1 from host memory: double-buffered 64 MiB chunks, H2D + kernel + D2H overlapped on two streams (each slot owns its
+// own keys / exchange scratch).  elem = 8: gr_complex; elem = 4: int16 I/Q, converted on the device right after the copy.
+static int demod_fft_host_any(lora_b200_decoder *d, const void *iq, size_t elem, float scale, size_t n_symbols, uint32_t *bins, float *mags) {
     if (!d || (!iq && n_symbols) || (!bins && n_symbols)) return fail(LORA_B200_EINVAL, "null argument");
     if (!d->k1_ok) return fail(LORA_B200_EUNSUPPORTED, "FFT demodulator needs samp_rate/bandwidth == 8 and SF7..SF12");
     CU(cudaSetDevice(d->device));
-    const size_t sym_bytes = sizeof(float2) * (size_t)d->sps;
+    const size_t sym_bytes = sizeof(float2) * (size_t)d->sps, sym_in = elem * (size_t)d->sps;
+    const bool sc16 = elem == 4;
     if (!d->chunk_symbols) {                          // lazily create the double-buffered pipeline (64 MiB chunks)
         d->chunk_symbols = std::max<size_t>(1, ((size_t)64 << 20) / sym_bytes);
         for (int i = 0; i < 2; i++) {
-            CU(cudaStreamCreateWithFlags(&d->copy_streams[i], cudaStreamNonBlocking));
+            if (!d->copy_streams[i]) CU(cudaStreamCreateWithFlags(&d->copy_streams[i], cudaStreamNonBlocking));
             CU(cudaMalloc(&d->d_chunk[i], d->chunk_symbols * sym_bytes));
             CU(cudaMalloc(&d->d_chunk_bins[i], d->chunk_symbols * sizeof(uint32_t)));
             CU(cudaMalloc(&d->d_chunk_mags[i], d->chunk_symbols * sizeof(float)));
         }
     }
+    if (sc16 && !d->d_chunk16[0])
+        for (int i = 0; i < 2; i++) CU(cudaMalloc(&d->d_chunk16[i], d->chunk_symbols * sym_in));
     cudaPointerAttributes attr;
     bool pinned = cudaPointerGetAttributes(&attr, iq) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -919,9 +988,18 @@ int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symb
         const int b = k & 1;
         cudaStream_t st = d->copy_streams[b];
         CU(cudaStreamSynchronize(st));                // buffer b is free again (its D2H finished)
-        const void *h = src + done * sym_bytes;
-        if (!pinned) { memcpy(d->h_chunk[b], h, n * sym_bytes); h = d->h_chunk[b]; }
-        CU(cudaMemcpyAsync(d->d_chunk[b], h, n * sym_bytes, cudaMemcpyHostToDevice, st));
+        const void *h = src + done * sym_in;
+        if (!pinned) { memcpy(d->h_chunk[b], h, n * sym_in); h = d->h_chunk[b]; }
+        if (sc16) {
+            CU(cudaMemcpyAsync(d->d_chunk16[b], h, n * sym_in, cudaMemcpyHostToDevice, st));
+            const size_t ns = n * (size_t)d->sps;
+            const int grid = (int)std::min<size_t>((ns / 4 + 255) / 256, (size_t)d->n_sms * 8);
+            sc16_to_cf32_kernel<<<grid, 256, 0, st>>>((const short2 *)d->d_chunk16[b], (float2 *)d->d_chunk[b], ns, scale);
+            d->launches++;
+            CU(cudaGetLastError());
+        } else {
+            CU(cudaMemcpyAsync(d->d_chunk[b], h, n * sym_bytes, cudaMemcpyHostToDevice, st));
+        }
         int rc = dispatch_k1(d, d->k1s[1 + b], (const float2 *)d->d_chunk[b], n, d->d_chunk_bins[b], d->d_chunk_mags[b], st);
         if (rc) return rc;
         CU(cudaMemcpyAsync(bins + done, d->d_chunk_bins[b], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -932,6 +1010,14 @@ int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symb
     CU(cudaStreamSynchronize(d->copy_streams[0]));
     CU(cudaStreamSynchronize(d->copy_streams[1]));
     return LORA_B200_OK;
+}
+
+int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, float *mags) {
+    return demod_fft_host_any(d, iq, sizeof(float2), 1.0f, n_symbols, bins, mags);
+}
+
+int lora_b200_demod_fft_host_sc16(lora_b200_decoder *d, const void *iq_sc16, float scale, size_t n_symbols, uint32_t *bins, float *mags) {
+    return demod_fft_host_any(d, iq_sc16, sizeof(short2), scale, n_symbols, bins, mags);
 }
 
 int lora_b200_demod_gradient_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols, uint32_t *bins, void *stream) {
@@ -972,16 +1058,19 @@ int lora_b200_deinterleave_dev(lora_b200_decoder *d, const uint32_t *words, uint
     return LORA_B200_OK;
 }
 
-// pinned host + device staging for the host-pointer entry points; grows on demand (calls are synchronous,
-// so one buffer serves every stream of a single-stream work() call)
-static int ensure_stage(lora_b200_decoder *d, size_t items) {
-    if (items <= d->stage_cap) return LORA_B200_OK;
-    if (d->d_stage) cudaFree(d->d_stage);
-    if (d->h_stage) cudaFreeHost(d->h_stage);
-    d->d_stage = nullptr; d->h_stage = nullptr; d->stage_cap = 0;
-    CU(cudaMalloc(&d->d_stage, sizeof(float2) * items));
-    CU(cudaMallocHost(&d->h_stage, sizeof(float2) * items));
-    d->stage_cap = items;
+// device staging for the host-pointer entry points (grows on demand); the pinned host mirror is only needed by the
+// single-stream work() call, whose caller's buffer is pageable GNU Radio memory
+static int ensure_stage(lora_b200_decoder *d, size_t items, bool want_host, bool want_sc16) {
+    if (items > d->stage_cap) {
+        if (d->d_stage) cudaFree(d->d_stage);
+        if (d->h_stage) cudaFreeHost(d->h_stage);
+        if (d->d_stage16) cudaFree(d->d_stage16);
+        d->d_stage = nullptr; d->h_stage = nullptr; d->d_stage16 = nullptr; d->stage_cap = 0;
+        CU(cudaMalloc(&d->d_stage, sizeof(float2) * items));
+        d->stage_cap = items;
+    }
+    if (want_host && !d->h_stage) CU(cudaMallocHost(&d->h_stage, sizeof(float2) * d->stage_cap));
+    if (want_sc16 && !d->d_stage16) CU(cudaMalloc(&d->d_stage16, sizeof(short2) * d->stage_cap));
     return LORA_B200_OK;
 }
 
@@ -993,32 +1082,65 @@ int lora_b200_work(lora_b200_decoder *d, uint32_t stream, const void *iq_host, s
     if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;     // never read past what was staged
     *consumed = 0;
     if (n_items < 2 * (size_t)d->sps) return LORA_B200_OK;                             // output_multiple, :91
-    int rc = ensure_stage(d, n_items);
+    int rc = ensure_stage(d, n_items, true, false);
     if (rc) return rc;
     memcpy(d->h_stage, iq_host, sizeof(float2) * n_items);
     CU(cudaMemcpyAsync(d->d_stage, d->h_stage, sizeof(float2) * n_items, cudaMemcpyHostToDevice, d->rx_stream));
     return run_rx(d, d->d_stage, n_items, n_items, stream, 1, consumed, cb, user);
 }
 
-int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, size_t stride_items, int host_ptr,
-                         size_t *consumed, lora_b200_frame_cb cb, void *user) {
+// all streams at once.  Host input is staged in groups of streams: the copy of group g + 1 (copy stream) runs under the
+// state machine of group g (rx stream), so the call costs max(PCIe, kernel) instead of their sum.  elem = 8: gr_complex,
+// elem = 4: interleaved int16 I/Q converted on the device (x * scale) before the state machine reads it.
+static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, float scale, size_t n_items, size_t stride_items,
+                          int host_ptr, size_t *consumed, lora_b200_frame_cb cb, void *user) {
     if (!d || !consumed || (!iq && n_items)) return fail(LORA_B200_EINVAL, "null argument");
     CU(cudaSetDevice(d->device));
     const uint32_t ns = d->cfg.n_streams;
     for (uint32_t s = 0; s < ns; s++) consumed[s] = 0;
     if (n_items < 2 * (size_t)d->sps) return LORA_B200_OK;
-    const float2 *dv = (const float2 *)iq;
-    size_t stride = stride_items;
-    if (host_ptr) {
-        if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;
-        int rc = ensure_stage(d, n_items * ns);
-        if (rc) return rc;
-        CU(cudaMemcpy2DAsync(d->d_stage, sizeof(float2) * n_items, iq, sizeof(float2) * stride_items,
-                             sizeof(float2) * n_items, ns, cudaMemcpyHostToDevice, d->rx_stream));
-        dv = d->d_stage;
-        stride = n_items;
+    const bool sc16 = elem == 4;
+    if (!host_ptr && !sc16) return run_rx(d, (const float2 *)iq, stride_items, n_items, 0, ns, consumed, cb, user);
+    if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;
+    int rc = ensure_stage(d, n_items * ns, false, sc16);
+    if (rc) return rc;
+    if (!d->copy_streams[0]) CU(cudaStreamCreateWithFlags(&d->copy_streams[0], cudaStreamNonBlocking));
+    const uint32_t n_groups = std::min<uint32_t>(ns, 8u), gs = (ns + n_groups - 1) / n_groups;
+    if (d->stage_events.size() < n_groups) {
+        const size_t have = d->stage_events.size();
+        d->stage_events.resize(n_groups, nullptr);
+        for (size_t i = have; i < n_groups; i++) CU(cudaEventCreateWithFlags(&d->stage_events[i], cudaEventDisableTiming));
     }
-    return run_rx(d, dv, stride, n_items, 0, ns, consumed, cb, user);
+    cudaStream_t cs = d->copy_streams[0];
+    if ((rc = rx_begin(d))) return rc;
+    for (uint32_t g = 0; g * gs < ns; g++) {
+        const uint32_t s0 = g * gs, cnt = std::min<uint32_t>(gs, ns - s0);
+        const uint8_t *src = (const uint8_t *)iq + (size_t)s0 * stride_items * elem;
+        void *dst = sc16 ? (void *)(d->d_stage16 + (size_t)s0 * n_items) : (void *)(d->d_stage + (size_t)s0 * n_items);
+        CU(cudaMemcpy2DAsync(dst, elem * n_items, src, elem * stride_items, elem * n_items, cnt,
+                             host_ptr ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
+        CU(cudaEventRecord(d->stage_events[g], cs));
+        CU(cudaStreamWaitEvent(d->rx_stream, d->stage_events[g], 0));
+        if (sc16) {
+            const size_t n = (size_t)cnt * n_items;
+            const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)d->n_sms * 8);
+            sc16_to_cf32_kernel<<<grid, 256, 0, d->rx_stream>>>(d->d_stage16 + (size_t)s0 * n_items, d->d_stage + (size_t)s0 * n_items, n, scale);
+            d->launches++;
+            CU(cudaGetLastError());
+        }
+        if ((rc = rx_launch(d, d->d_stage + (size_t)s0 * n_items, n_items, n_items, s0, cnt))) return rc;
+    }
+    return rx_finish(d, 0, ns, consumed, cb, user);
+}
+
+int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, size_t stride_items, int host_ptr,
+                         size_t *consumed, lora_b200_frame_cb cb, void *user) {
+    return work_batch_any(d, iq, sizeof(float2), 1.0f, n_items, stride_items, host_ptr, consumed, cb, user);
+}
+
+int lora_b200_work_batch_sc16(lora_b200_decoder *d, const void *iq_sc16, float scale, size_t n_items, size_t stride_items,
+                              int host_ptr, size_t *consumed, lora_b200_frame_cb cb, void *user) {
+    return work_batch_any(d, iq_sc16, sizeof(short2), scale, n_items, stride_items, host_ptr, consumed, cb, user);
 }
 
 int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream) {

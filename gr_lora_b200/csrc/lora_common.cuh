@@ -34,17 +34,20 @@ LB_D float2 cadd(float2 a, float2 b) { return up2(add2(pk2(a.x, a.y), pk2(b.x, b
 LB_D float2 csub(float2 a, float2 b) { return up2(sub2(pk2(a.x, a.y), pk2(b.x, b.y))); }
 // packed product with a compile-time constant (used inside the radix butterflies)
 LB_D float2 cmul_const(float2 a, float wx, float wy) {
-    return up2(fma2(pk2(a.x, a.x), pk2(wx, wy), mul2(pk2(a.y, a.y), pk2(-wy, wx))));
+    return up2(fma2(pk2(wx, wy), pk2(a.x, a.x), mul2(pk2(-wy, wx), pk2(a.y, a.y))));
 }
 #ifdef LB_PACKED_CMUL
 // plain complex product (the reference multiplies by the down-chirp, not its conjugate,
-// lib/decoder_impl.cc:436-438):  a*b = a.x*(b.x, b.y) + a.y*(-b.y, b.x)
+// lib/decoder_impl.cc:436-438):  a*b = (b.x, b.y)*a.x + (-b.y, b.x)*a.y
+// Operand ORDER matters: with the swapped / half-negated pair as the FIRST multiplicand ptxas folds the swap and the sign
+// into operand modifiers (FMUL2 R, -Rb.F32x2.LO_HI.NP, Ra.F32), so a complex product is exactly two instructions; with
+// the broadcast first it materialises the pair with a MOV and an FADD (measured on the SASS, profiles/r2_cmul_sass.md).
 LB_D float2 cmul(float2 a, float2 b) {
-    return up2(fma2(pk2(a.x, a.x), pk2(b.x, b.y), mul2(pk2(a.y, a.y), pk2(-b.y, b.x))));
+    return up2(fma2(pk2(b.x, b.y), pk2(a.x, a.x), mul2(pk2(-b.y, b.x), pk2(a.y, a.y))));
 }
 // a * w + c
 LB_D float2 cfma(float2 a, float2 w, float2 c) {
-    return up2(fma2(pk2(a.x, a.x), pk2(w.x, w.y), fma2(pk2(a.y, a.y), pk2(-w.y, w.x), pk2(c.x, c.y))));
+    return up2(fma2(pk2(w.x, w.y), pk2(a.x, a.x), fma2(pk2(-w.y, w.x), pk2(a.y, a.y), pk2(c.x, c.y))));
 }
 LB_D float cnorm2(float2 a) { const float2 q = up2(mul2(pk2(a.x, a.y), pk2(a.x, a.y))); return q.x + q.y; }
 #endif

@@ -128,9 +128,15 @@ class decoder:
         self._emit_stdout(stream)
         return int(consumed.value)
 
-    def work_batch(self, iq, n_items=None, stride_items=None, host=None):
-        """All streams at once. ``iq``: host ndarray [n_streams, n_items] or a device tensor/pointer."""
-        if isinstance(iq, np.ndarray):
+    def work_batch(self, iq, n_items=None, stride_items=None, host=None, sc16_scale=None):
+        """All streams at once. ``iq``: host ndarray [n_streams, n_items] (complex64, or int16 [n_streams, n_items, 2]
+        together with ``sc16_scale``) or a device tensor/pointer.  ``sc16_scale`` selects the int16 I/Q entry point:
+        the device computes x * scale, PCIe moves 4 bytes per sample."""
+        if isinstance(iq, np.ndarray) and sc16_scale is not None:
+            x = np.ascontiguousarray(iq, dtype=np.int16)
+            assert x.ndim == 3 and x.shape[0] == self.n_streams and x.shape[2] == 2
+            ptr, n_items, stride_items, host = x.ctypes.data, x.shape[1], x.shape[1], 1
+        elif isinstance(iq, np.ndarray):
             x = np.ascontiguousarray(iq, dtype=np.complex64)
             assert x.ndim == 2 and x.shape[0] == self.n_streams
             ptr, n_items, stride_items, host = x.ctypes.data, x.shape[1], x.shape[1], 1
@@ -140,8 +146,12 @@ class decoder:
             if stride_items is None:
                 stride_items = n_items
         consumed = (C.c_size_t * self.n_streams)()
-        N.check(self._L.lora_b200_work_batch(self._h, ptr, int(n_items), int(stride_items), host, consumed, self._cb, None),
-                "lora_b200_work_batch")
+        if sc16_scale is not None:
+            N.check(self._L.lora_b200_work_batch_sc16(self._h, ptr, float(sc16_scale), int(n_items), int(stride_items), host,
+                                                      consumed, self._cb, None), "lora_b200_work_batch_sc16")
+        else:
+            N.check(self._L.lora_b200_work_batch(self._h, ptr, int(n_items), int(stride_items), host, consumed, self._cb, None),
+                    "lora_b200_work_batch")
         for s in range(self.n_streams):
             self._emit_stdout(s)
         return np.array(list(consumed), dtype=np.int64)
@@ -198,6 +208,20 @@ class decoder:
         bp = bins.ctypes.data if isinstance(bins, np.ndarray) else int(bins)
         mp = mags.ctypes.data if isinstance(mags, np.ndarray) else int(mags)
         N.check(self._L.lora_b200_demod_fft_host(self._h, ptr, n, bp, mp), "lora_b200_demod_fft_host")
+        return bins, mags
+
+    def demod_fft_host_sc16(self, iq_sc16, scale, bins_out=None, mags_out=None):
+        """K1 end to end from int16 I/Q host memory. iq_sc16: int16 ndarray [..., 2] or (ptr, n_symbols)."""
+        if isinstance(iq_sc16, tuple):
+            ptr, n = int(iq_sc16[0]), int(iq_sc16[1])
+        else:
+            x = np.ascontiguousarray(iq_sc16, dtype=np.int16)
+            ptr, n = x.ctypes.data, x.size // (2 * self.sps)
+        bins = np.empty(n, np.uint32) if bins_out is None else bins_out
+        mags = np.empty(n, np.float32) if mags_out is None else mags_out
+        bp = bins.ctypes.data if isinstance(bins, np.ndarray) else int(bins)
+        mp = mags.ctypes.data if isinstance(mags, np.ndarray) else int(mags)
+        N.check(self._L.lora_b200_demod_fft_host_sc16(self._h, ptr, float(scale), n, bp, mp), "lora_b200_demod_fft_host_sc16")
         return bins, mags
 
     def demod_gradient(self, iq_dev, n_symbols, bins_dev, cuda_stream=0):

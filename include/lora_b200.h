@@ -121,6 +121,11 @@ int lora_b200_demod_fft_dev(lora_b200_decoder *d, const void *iq, size_t n_symbo
                             uint32_t *bins, float *mags, void *cuda_stream);
 int lora_b200_demod_fft_host(lora_b200_decoder *d, const void *iq, size_t n_symbols,
                              uint32_t *bins, float *mags);
+/* SDR-native ingest: iq_sc16 = interleaved little-endian int16 I/Q (what a USRP / file source delivers before the
+ * host-side conversion to gr_complex); the device converts x * scale right after the copy, so PCIe moves 4 instead of
+ * 8 bytes per sample.  Results equal lora_b200_demod_fft_host on the host-converted buffer bit for bit. */
+int lora_b200_demod_fft_host_sc16(lora_b200_decoder *d, const void *iq_sc16, float scale, size_t n_symbols,
+                                  uint32_t *bins, float *mags);
 /* K2: max_frequency_gradient_idx on aligned windows (:466-491), same layout */
 int lora_b200_demod_gradient_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols,
                                  uint32_t *bins, void *cuda_stream);
@@ -149,6 +154,10 @@ int lora_b200_work(lora_b200_decoder *d, uint32_t stream, const void *iq_host, s
  * host_ptr != 0: iq is host memory (copied inside); 0: iq is device memory. */
 int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, size_t stride_items,
                          int host_ptr, size_t *consumed /* [n_streams] */, lora_b200_frame_cb cb, void *user);
+/* the same with int16 I/Q input (see lora_b200_demod_fft_host_sc16); frames, consume amounts and stdout equal those of
+ * lora_b200_work_batch on the host-converted buffer. */
+int lora_b200_work_batch_sc16(lora_b200_decoder *d, const void *iq_sc16, float scale, size_t n_items, size_t stride_items,
+                              int host_ptr, size_t *consumed /* [n_streams] */, lora_b200_frame_cb cb, void *user);
 /* current state of a stream (LORA_B200_DETECT ...) */
 int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream);
 /* the reference's std::cout hex lines for the frames delivered by the last work call of this

@@ -20,6 +20,7 @@ def emul():
     L.lb_k1_emulate.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lb_k1_emulate_warp_sf7.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lb_k1_emulate_group.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.lb_k1_emulate_rows.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lb_k1_emulate_big.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lb_k1_emulate_ab.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.lb_k1_emulate_xchg.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -167,3 +168,24 @@ def test_tx_inverts_the_integer_chain(emul):
                 assert got == payload
             else:
                 assert got == payload
+
+
+@pytest.mark.parametrize("sf", [11, 12])
+def test_k1_rows_emulation_matches_oracle(emul, oracle, sf):
+    """k1_rows.cuh (SF11: one CTA per symbol; SF12: two CTAs, branches 4c..4c+3 each): the rotating slot pool, the in-place
+    swizzled passes, the lane-pair and CTA-pair partial sums and the bin-N/2 double evaluation, thread by thread on the
+    host; edge bins and noise down to -14 dB."""
+    d = oracle.Decoder(sf=sf)
+    nb = 1 << sf
+    chirp, tw = d.downchirp, twiddle_table(d.sps)
+    rng = np.random.default_rng(sf)
+    n = 40                                     # more than two turns of the 28 / 26-slot pool
+    vals = rng.integers(0, nb, n)
+    vals[:6] = [0, 1, nb // 2 - 1, nb // 2, nb // 2 + 1, nb - 1]
+    for snr in (None, -3.0, -14.0):
+        x = tx.synth_symbols(vals, sf, snr_db=snr, seed=5)
+        bins, mags = np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        assert emul.lb_k1_emulate_rows(sf, x.ctypes.data, n, chirp.ctypes.data, tw.ctypes.data, bins.ctypes.data, mags.ctypes.data) == 0
+        ob, om = d.demod_fft_batch(x)
+        assert np.array_equal(bins, ob)
+        np.testing.assert_allclose(mags, om, rtol=2e-6)

@@ -65,7 +65,7 @@ def main():
     out = {"sf": sf, "env": {k: v for k, v in os.environ.items() if k.startswith("LORA_B200_")}}
     stream = torch.cuda.current_stream()
     if not args.no_parity:
-        n = args.parity_symbols or {10: 907, 11: 461, 12: 233}.get(sf, 300)
+        n = args.parity_symbols or {7: 7111, 8: 3559, 9: 1783, 10: 907, 11: 607, 12: 461}.get(sf, 300)
         rng = np.random.default_rng(sf)
         vals = rng.integers(0, nb, n)
         vals[:6] = [0, 1, nb // 2 - 1, nb // 2, nb // 2 + 1, nb - 1]
