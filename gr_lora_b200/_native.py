@@ -58,6 +58,8 @@ SIGNATURES = {
     "lora_b200_work_batch": (_i, [_vp, _vp, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_work_batch_sc16": (_i, [_vp, _vp, C.c_float, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_stream_state": (_i, [_vp, _u32]),
+    "lora_b200_set_cfo_estimate": (_i, [_vp, _i]),
+    "lora_b200_last_cfo": (_i, [_vp, _u32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "lora_b200_stdout_last": (_i, [_vp, _u32, C.c_char_p, _sz]),
     "lora_b200_trace_read": (_i, [_vp, _u32, C.POINTER(Step), _sz, C.POINTER(_sz)]),
     "lora_b200_launch_count": (C.c_uint64, [_vp]),
@@ -67,9 +69,11 @@ SIGNATURES = {
     "lora_b200_channelizer_ntaps": (_u32, [_vp]),
     "lora_b200_channelizer_taps": (_i, [_vp, C.POINTER(C.c_float), _sz]),
     "lora_b200_channelizer_apply_cfo": (_i, [_vp, _u32, C.c_float]),
+    "lora_b200_channelizer_set_conjugate": (_i, [_vp, _i]),
     "lora_b200_channelizer_work_dev": (_i, [_vp, _vp, _sz, _vp, _sz, C.POINTER(_sz), _vp]),
     "lora_b200_channelizer_work_host": (_i, [_vp, _vp, _sz, C.POINTER(_sz)]),
     "lora_b200_channelizer_output": (_vp, [_vp, _u32, C.POINTER(_sz)]),
+    "lora_b200_channelizer_read_output": (_i, [_vp, _u32, _vp, _sz]),
     "lora_b200_channelizer_launch_count": (C.c_uint64, [_vp]),
 }
 

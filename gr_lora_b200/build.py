@@ -98,5 +98,22 @@ def build_shim(force: bool = False) -> Path:
     return SHIM
 
 
+CHAN_SHIM = ROOT / "build" / "chan_shim_demo"
+
+
+def build_chan_shim(force: bool = False) -> Path:
+    """The C++ drop-in body of gr::lora::channelizer_impl (host/channelizer_impl.cc) + a file-in / file-out main."""
+    host = PKG / "host"
+    srcs = [host / "channelizer_impl.cc", host / "chan_shim_main.cc", host / "channelizer_impl.h", host / "lora" / "channelizer.h",
+            host / "gr_stub" / "gnuradio" / "hier_block2.h", host / "gr_stub" / "gnuradio" / "sync_block.h", ROOT / "include" / "lora_b200.h"]
+    build()
+    if force or _stale(CHAN_SHIM, srcs) or CHAN_SHIM.stat().st_mtime < LIB.stat().st_mtime:
+        CHAN_SHIM.parent.mkdir(exist_ok=True)
+        cmd = ["g++", "-O2", "-std=c++17", "-I", str(host / "gr_stub"), "-I", str(host), "-I", str(ROOT / "include"), "-o", str(CHAN_SHIM),
+               str(host / "channelizer_impl.cc"), str(host / "chan_shim_main.cc"), "-L", str(PKG), "-llora_b200", f"-Wl,-rpath,{PKG}"]
+        subprocess.run(cmd, check=True)
+    return CHAN_SHIM
+
+
 if __name__ == "__main__":
     print(build(verbose=True))

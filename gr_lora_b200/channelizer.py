@@ -56,6 +56,10 @@ class channelizer:
     def apply_cfo(self, cfo, channel=0):
         self._check(self._L.lora_b200_channelizer_apply_cfo(self._h, int(channel), float(cfo)), "channelizer_apply_cfo")
 
+    def set_conjugate(self, on=True):
+        """Conjugate every output sample on the device (lora_receiver's optional conjugate_cc, python/lora_receiver.py:70-75)."""
+        self._check(self._L.lora_b200_channelizer_set_conjugate(self._h, int(bool(on))), "channelizer_set_conjugate")
+
     def work(self, samples) -> int:
         """Filter a host buffer (length a multiple of the decimation); the result stays on the device.
         Returns the number of output items per channel."""

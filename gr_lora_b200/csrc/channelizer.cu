@@ -34,6 +34,7 @@ struct lora_b200_channelizer {
     float2 *d_in = nullptr, *d_out = nullptr;     // internal staging for the host entry point
     size_t in_cap = 0, out_cap = 0;               // items
     uint64_t launches = 0;
+    bool conj_out = false;                        // conjugate every output sample (the hier block's optional conjugate_cc)
     std::string err;
 };
 
@@ -45,7 +46,7 @@ constexpr int CH_CT = 4;        // channels per block (register accumulators)
 __global__ void __launch_bounds__(CH_TN)
 chan_fir_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, size_t n_in, uint32_t D, uint32_t ntaps,
                 const float2 *__restrict__ ctaps, const double *__restrict__ phase0, const double *__restrict__ dphase,
-                float2 *__restrict__ out, size_t out_stride, size_t n_out, uint32_t n_channels) {
+                float2 *__restrict__ out, size_t out_stride, size_t n_out, uint32_t n_channels, float conj_sign) {
     extern __shared__ float2 ch_smem[];
     const uint32_t seg = (CH_TN - 1) * D + ntaps;            // input samples this tile needs
     float2 *xs = ch_smem;                                     // [seg]
@@ -88,7 +89,8 @@ chan_fir_kernel(const float2 *__restrict__ hist, const float2 *__restrict__ x, s
                 double s, co;
                 sincos(phase0[ch] + dphase[ch] * (double)n, &s, &co);   // rotator e^{-j w D n}, phase kept in double
                 const float cr = (float)co, sr = (float)s;
-                out[(size_t)ch * out_stride + n] = make_float2(acc[c].x * cr - acc[c].y * sr, acc[c].x * sr + acc[c].y * cr);
+                // conj_sign = -1: the blocks.conjugate_cc the reference wires between channelizer and decoder (python/lora_receiver.py:70-75)
+                out[(size_t)ch * out_stride + n] = make_float2(acc[c].x * cr - acc[c].y * sr, conj_sign * (acc[c].x * sr + acc[c].y * cr));
             }
         }
     }
@@ -177,6 +179,12 @@ int lora_b200_channelizer_taps(const lora_b200_channelizer *c, float *out, size_
     return (int)c->ntaps;
 }
 
+int lora_b200_channelizer_set_conjugate(lora_b200_channelizer *c, int on) {
+    if (!c) return cfail(c, LORA_B200_EINVAL, "channelizer_set_conjugate: null argument");
+    c->conj_out = on != 0;
+    return LORA_B200_OK;
+}
+
 int lora_b200_channelizer_apply_cfo(lora_b200_channelizer *c, uint32_t channel, float cfo) {   // channelizer_impl::apply_cfo :68-71
     if (!c || channel >= c->n_channels) return cfail(c, LORA_B200_EINVAL, "channelizer_apply_cfo: bad channel");
     cudaSetDevice(c->device);
@@ -212,7 +220,7 @@ int lora_b200_channelizer_work_dev(lora_b200_channelizer *c, const void *in_dev,
     if (smem > 200 * 1024) return cfail(c, LORA_B200_EUNSUPPORTED, "channelizer_work: filter too long for one tile");
     dim3 grid((unsigned)((no + CH_TN - 1) / CH_TN), (c->n_channels + CH_CT - 1) / CH_CT);
     chan_fir_kernel<<<grid, CH_TN, smem, st>>>(c->d_hist, (const float2 *)in_dev, n_in, c->decimation, c->ntaps, c->d_ctaps,
-                                              c->d_phase, c->d_dphase, (float2 *)out_dev, out_stride, no, c->n_channels);
+                                              c->d_phase, c->d_dphase, (float2 *)out_dev, out_stride, no, c->n_channels, c->conj_out ? -1.0f : 1.0f);
     c->launches++;
     if (cudaGetLastError() != cudaSuccess) return cfail(c, LORA_B200_ECUDA, "channelizer_work: launch failed");
     // history for the next call: the last ntaps-1 samples of (history ++ input)
@@ -260,6 +268,15 @@ const void *lora_b200_channelizer_output(const lora_b200_channelizer *c, uint32_
     if (!c || channel >= c->n_channels || !c->d_out) return nullptr;
     if (stride_items) *stride_items = c->out_cap;
     return c->d_out + (size_t)channel * c->out_cap;
+}
+
+int lora_b200_channelizer_read_output(const lora_b200_channelizer *c, uint32_t channel, void *host_dst, size_t n_items) {
+    if (!c || channel >= c->n_channels || !c->d_out || (!host_dst && n_items)) return cfail(nullptr, LORA_B200_EINVAL, "channelizer_read_output: bad argument");
+    if (n_items > c->out_cap) return cfail(nullptr, LORA_B200_EINVAL, "channelizer_read_output: more items than the last call produced");
+    cudaSetDevice(c->device);
+    if (n_items && cudaMemcpy(host_dst, c->d_out + (size_t)channel * c->out_cap, sizeof(float2) * n_items, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return cfail(nullptr, LORA_B200_ECUDA, "channelizer_read_output: D2H failed");
+    return LORA_B200_OK;
 }
 
 uint64_t lora_b200_channelizer_launch_count(const lora_b200_channelizer *c) { return c ? c->launches : 0; }

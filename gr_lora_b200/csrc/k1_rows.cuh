@@ -59,6 +59,10 @@ struct RCfg {
 };
 
 constexpr int R_NSYM_BAR = 4;                            // symbol barriers in rotation (<= 2.75 symbols in flight)
+// Rows of the next symbol that have to wait for slots of the current one are always its LAST ones (NSLOT - 16 rows are
+// prefetched into free slots).  They get their own barrier: pass 0 loads and dechirps the early rows first and only then
+// waits for the late ones (second capture: 8.8 % of all samples sat in the single wait at the top of the loop).
+template <int SF> struct RLate { static constexpr int EARLY = RCfg<SF>::NSLOT - 16; };      // 12 (SF11) / 8 (SF12) early rows
 
 // tensor-memory columns of one thread (lane = 32 (warp & 3) + lane):
 //   chirp   [64 (warp >> 2), +64)        c[j][b] of the thread's pass-0 samples, word 4 j + 2 b + {re, im}
@@ -197,6 +201,14 @@ LB_D void st_peer_f2(uint32_t peer_addr, float2 v) {
 LB_D void mbar_arrive_peer(uint32_t peer_bar_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar_addr) : "memory");
 }
+LB_D void mbar_arrive_peer_relaxed(uint32_t peer_bar_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar_addr) : "memory");
+}
+// shared::cta -> the peer CTA's shared memory through the async proxy; the bytes are counted on the PEER's mbarrier
+LB_D void bulk_s2peer(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_bar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(peer_dst), "r"(local_src), "r"(bytes), "r"(peer_bar) : "memory");
+}
 LB_D void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // acquire at cluster scope: the peer's DSMEM stores are visible after it
     uint32_t ok;
     do {
@@ -218,9 +230,13 @@ LB_D void tma_rows_2d(void *dst_smem, const void *tmap, int c0, int c1, uint64_t
 template <int SF>
 struct RSmem {
     float4 slots[RCfg<SF>::NSLOT][RCfg<SF>::ROW_F4];
-    float2 recv[RCfg<SF>::CL == 2 ? 2048 + 8 : 8];      // peer partial sums [kc & 7][kb][h][8] (+ the bin-N/2 extra), SF12 only
+    // SF12 only: partial sums of the bins the PEER finishes, per warp pair a block of [kb][h][8] complex + the bin-N/2 extra
+    // (258 complex = 2064 bytes): staged in `send`, moved by cp.async.bulk into the peer's `recv`
+    float2 recv[RCfg<SF>::CL == 2 ? 8 * 258 : 2];
+    float2 send[RCfg<SF>::CL == 2 ? 8 * 258 : 2];
     unsigned long long keys[2][RCfg<SF>::NW];
-    uint64_t sym_full[R_NSYM_BAR];
+    uint64_t sym_full[R_NSYM_BAR];                        // early rows of a symbol
+    uint64_t sym_late[R_NSYM_BAR];                        // its last 16 - EARLY rows
     uint64_t x_full[8], x_free[8];                        // SF12: per receiving / sending warp pair
     uint32_t tm_base;
 };
@@ -250,9 +266,12 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
 
     if (tid == 0) {
 #pragma unroll
-        for (int i = 0; i < R_NSYM_BAR; i++) mbar_init(&sm.sym_full[i], 16);
+        for (int i = 0; i < R_NSYM_BAR; i++) { mbar_init(&sm.sym_full[i], RLate<SF>::EARLY); mbar_init(&sm.sym_late[i], 16 - RLate<SF>::EARLY); }
 #pragma unroll
-        for (int i = 0; i < 8; i++) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_free[i], 1); }
+        for (int i = 0; i < 8; i++) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_free[i], 32); }     // full: one expect_tx + the copy's bytes; free: every lane
+        if (C::CL == 2 && n_mine > 0)
+#pragma unroll
+            for (int i = 0; i < 8; i++) mbar_expect_tx(&sm.x_full[i], 258u * 8u);     // phase 0 of the receive barriers
         fence_mbar_init();
     }
     if (warp == 0) tm_alloc(&sm.tm_base);
@@ -267,7 +286,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         if (s >= n_mine) return;
         const int j = (int)(g & 15);
         const size_t sym = unit + s * n_units;
-        uint64_t *bar = &sm.sym_full[s % R_NSYM_BAR];
+        uint64_t *bar = j < RLate<SF>::EARLY ? &sm.sym_full[s % R_NSYM_BAR] : &sm.sym_late[s % R_NSYM_BAR];
         float4 *dst = sm.slots[g % C::NSLOT];
         mbar_expect_tx(bar, C::ROW_BYTES);
         if (C::CL == 1) bulk_g2s(dst, a.x + sym * C::SPS + (size_t)j * (C::SPS / 16), C::ROW_BYTES, bar);
@@ -352,6 +371,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
             float2 v0[16], v1[16], tw[16];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
+                if (4 * q == RLate<SF>::EARLY) mbar_wait(&sm.sym_late[s % R_NSYM_BAR], (uint32_t)((s / R_NSYM_BAR) & 1));
                 float2 ch[8];
                 tm_ld16(tm_lane + (uint32_t)(R_TM_CHIRP + 64 * (warp >> 2) + 16 * q), ch);
                 float4 xv[4];
@@ -483,30 +503,41 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 tq = cadd(tq, got);
             }
             if (C::CL == 2) {
-                // bins of rows kc < 8 are finished by CTA 0, kc >= 8 by CTA 1: the other CTA sends its partial sums
+                // bins of rows kc < 8 are finished by CTA 0, kc >= 8 by CTA 1: the other CTA sends its partial sums.  The
+                // block travels through the async proxy (cp.async.bulk shared::cta -> shared::cluster, complete_tx on the
+                // peer's mbarrier), so the receiver needs no cluster-scope acquire and the sender no cluster-scope fence: in
+                // the first version those compiled to MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL and held 30 % of all stall samples.
                 const int xi = warp & 7;
                 const bool mine = (uint32_t)(warp >> 3) == rank;
-                const int ridx = ((xi * 16 + kb2) * 2 + h2) * 8;
+                const int ridx = xi * 258 + (kb2 * 2 + h2) * 8;
                 if (!mine) {
-                    if (s > 0) mbar_wait_cluster(&sm.x_free[xi], (uint32_t)((s - 1) & 1));     // the peer has read the previous symbol's sums
-                    const uint32_t dst = map_to_peer(smem_u32(&sm.recv[ridx]), peer);
+                    if (s > 0) mbar_wait(&sm.x_free[xi], (uint32_t)((s - 1) & 1));     // the peer has consumed the previous block (so the copy has read `send`)
+                    float4 *dst = reinterpret_cast<float4 *>(&sm.send[ridx]);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) st_peer_f4(dst + 16u * i, make_float4(f[2 * i].x, f[2 * i].y, f[2 * i + 1].x, f[2 * i + 1].y));
-                    if (quirk_warp && lane == 1) st_peer_f2(map_to_peer(smem_u32(&sm.recv[2048]), peer), tq);
-                    fence_cluster();
+                    for (int i = 0; i < 4; i++) dst[i] = make_float4(f[2 * i].x, f[2 * i].y, f[2 * i + 1].x, f[2 * i + 1].y);
+                    if (quirk_warp && lane == 1) sm.send[xi * 258 + 256] = tq;
+                    fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive_peer(map_to_peer(smem_u32(&sm.x_full[xi]), peer));
+                    if (lane == 0)
+                        bulk_s2peer(map_to_peer(smem_u32(&sm.recv[xi * 258]), peer), smem_u32(&sm.send[xi * 258]), 258u * 8u,
+                                    map_to_peer(smem_u32(&sm.x_full[xi]), peer));
                 } else {
-                    mbar_wait_cluster(&sm.x_full[xi], (uint32_t)(s & 1));
+                    mbar_wait(&sm.x_full[xi], (uint32_t)(s & 1));
+                    uint32_t dep = 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const float4 u = *reinterpret_cast<const float4 *>(&sm.recv[ridx + 2 * i]);
                         f[2 * i] = cadd(f[2 * i], make_float2(u.x, u.y));
                         f[2 * i + 1] = cadd(f[2 * i + 1], make_float2(u.z, u.w));
+                        dep |= __float_as_uint(u.w);
                     }
-                    if (quirk_warp && lane == 1) tq = cadd(tq, sm.recv[2048]);
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_peer(map_to_peer(smem_u32(&sm.x_free[xi]), peer));
+                    if (quirk_warp && lane == 1) tq = cadd(tq, sm.recv[xi * 258 + 256]);
+                    if (quirk_warp && lane == 1) dep |= __float_as_uint(tq.x);
+                    if (lane == 0 && s + 1 < n_mine) mbar_expect_tx(&sm.x_full[xi], 258u * 8u);      // arm the next phase (this one has completed)
+                    // tell the peer the block has been read: the arrive carries no data (relaxed), but it must not be
+                    // issued before this lane's loads have returned, so its address depends on them
+                    asm volatile("and.b32 %0, %0, 0;" : "+r"(dep));
+                    mbar_arrive_peer_relaxed(map_to_peer(smem_u32(&sm.x_free[xi]), peer) + dep);
                 }
                 if (mine) {
                     if (quirk_warp && lane == 1) f[0] = cadd(f[0], tq);

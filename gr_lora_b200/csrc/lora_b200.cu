@@ -108,6 +108,7 @@ struct lora_b200_decoder {
     std::vector<RxFrameOut> h_frames;
     std::vector<std::string> stdout_last;
     uint64_t launches = 0;
+    bool cfo_estimate = false;            // lora_b200_set_cfo_estimate
 };
 
 namespace {
@@ -678,6 +679,7 @@ int rx_launch(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, siz
     p.down_ifreq_avg = d->down_ifreq_avg; p.down_ifreq_sd = d->down_ifreq_sd;
     p.sps = d->sps; p.n_bins = d->n_bins; p.n_bins_hdr = d->n_bins_hdr; p.decim = d->decim; p.sf = d->cfg.sf;
     p.implicit = d->cfg.implicit; p.reduced_rate = d->cfg.reduced_rate; p.enable_fine_sync = !d->cfg.disable_drift_correction;
+    p.cfo_estimate = d->cfo_estimate ? 1 : 0; p.samples_per_second = (float)d->samples_per_second;
     p.states = d->d_states; p.scratch = d->d_scratch; p.consumed = d->d_consumed;
     p.frames = d->d_frames; p.n_frames = d->d_n_frames; p.frame_cap = d->frame_cap;
     p.max_frames_per_stream = d->cfg.max_frames_per_call;
@@ -1149,6 +1151,22 @@ int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream) {
     int32_t st = 0;
     CU(cudaMemcpy(&st, &d->d_states[stream].state, sizeof st, cudaMemcpyDeviceToHost));
     return st;
+}
+
+int lora_b200_set_cfo_estimate(lora_b200_decoder *d, int enable) {
+    if (!d) return fail(LORA_B200_EINVAL, "null argument");
+    d->cfo_estimate = enable != 0;
+    return LORA_B200_OK;
+}
+
+int lora_b200_last_cfo(lora_b200_decoder *d, uint32_t stream, float *cfo_hz, uint32_t *count) {
+    if (!d || stream >= d->cfg.n_streams || !cfo_hz) return fail(LORA_B200_EINVAL, "bad argument");
+    CU(cudaSetDevice(d->device));
+    struct { float cfo; uint32_t n; } v;
+    CU(cudaMemcpy(&v, &d->d_states[stream].cfo_est, sizeof v, cudaMemcpyDeviceToHost));
+    *cfo_hz = v.cfo;
+    if (count) *count = v.n;
+    return LORA_B200_OK;
 }
 
 int lora_b200_stdout_last(lora_b200_decoder *d, uint32_t stream, char *buf, size_t cap) {

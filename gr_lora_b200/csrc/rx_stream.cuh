@@ -44,6 +44,8 @@ struct RxStreamState {                 // members of decoder_impl, lib/decoder_i
     uint8_t n_hdr_print;
     uint8_t hdr_print[4];
     uint8_t demodulated[LB_MAX_CW];
+    float cfo_est;                     // experimental_determine_cfo at the last SYNC (Hz), only with cfo_estimate enabled
+    uint32_t cfo_count;                // how many estimates this stream has produced
 };
 
 struct RxFrameRec {                    // one completed frame, input of the K8 kernel
@@ -76,6 +78,8 @@ struct RxParams {
     // derived configuration (decoder_impl.cc:69-91)
     uint32_t sps, n_bins, n_bins_hdr, decim, sf;
     int implicit, reduced_rate, enable_fine_sync;
+    int cfo_estimate;                  // 1: also run experimental_determine_cfo (:730-738) where the reference has its call commented out (:774)
+    float samples_per_second;
     // state / outputs
     RxStreamState *states;
     float *scratch;                    // per stream 2*sps + n_bins floats
@@ -290,6 +294,18 @@ rx_stream_kernel(RxParams p) {
                 sh.metric = best ? key_mag2(best) : 0.0f;
                 sh.consumed = best ? (int)key_idx(best) : 0;      // :780 consume_each(i)
                 sh.state = LORA_B200_FIND_SFD;
+                if (p.cfo_estimate && sps > 257) {
+                    // experimental_determine_cfo(&input[i], sps) (:730-738, call site :774 commented out in the reference):
+                    // instantaneous frequency of samples * downchirp at the hard-coded index 256, in Hz
+                    const float2 *xi = x + sh.consumed;
+                    const float2 m0 = cmul(xi[256], __ldg(p.down + 256)), m1 = cmul(xi[257], __ldg(p.down + 257));
+                    const float p1 = atan2f(m0.y, m0.x);
+                    float p2 = atan2f(m1.y, m1.x);
+                    while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
+                    while ((double)(p2 - p1) < -3.14159265358979323846) p2 = (float)((double)p2 + 6.283185307179586);
+                    st->cfo_est = (float)((double)(p2 - p1) / (2.0 * 3.14159265358979323846) * (double)p.samples_per_second);
+                    st->cfo_count++;
+                }
             }
             break;
         }

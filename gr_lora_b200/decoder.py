@@ -177,6 +177,16 @@ class decoder:
             pos += c
         return pos
 
+    def set_cfo_estimate(self, enable=True):
+        """Also run the reference's experimental_determine_cfo at every SYNC (lib/decoder_impl.cc:730-738,774); off by default."""
+        N.check(self._L.lora_b200_set_cfo_estimate(self._h, int(bool(enable))), "lora_b200_set_cfo_estimate")
+
+    def last_cfo(self, stream=0):
+        """(latest CFO estimate in Hz, number of estimates so far) of a stream."""
+        cfo, n = C.c_float(0.0), C.c_uint32(0)
+        N.check(self._L.lora_b200_last_cfo(self._h, int(stream), C.byref(cfo), C.byref(n)), "lora_b200_last_cfo")
+        return float(cfo.value), int(n.value)
+
     def state(self, stream=0):
         return N.check(self._L.lora_b200_stream_state(self._h, int(stream)), "lora_b200_stream_state")
 

@@ -11,7 +11,8 @@ from .decoder import decoder
 
 class lora_receiver:
     def __init__(self, samp_rate, center_freq, channel_list, bandwidth, sf, implicit, cr, crc, reduced_rate=False,
-                 conj=False, decimation=1, disable_channelization=False, disable_drift_correction=False, **decoder_kw):
+                 conj=False, decimation=1, disable_channelization=False, disable_drift_correction=False, cfo_feedback=False,
+                 **decoder_kw):
         self.samp_rate, self.center_freq, self.channel_list = samp_rate, center_freq, list(channel_list)
         self.bandwidth, self.sf, self.implicit, self.cr, self.crc = bandwidth, sf, implicit, cr, crc
         self.decimation, self.conj = decimation, conj
@@ -23,12 +24,24 @@ class lora_receiver:
             from .channelizer import channelizer
             self.channelizer = channelizer(samp_rate, center_freq, self.channel_list, bandwidth, decimation,
                                            device=decoder_kw.get("device", -1))
+            if conj:                                 # channelizer -> conjugate_cc -> decoder (:62-63,70-75), conjugated on the device
+                self.channelizer.set_conjugate(True)
         if disable_channelization and decimation != 1:
             raise NotImplementedError("fractional_resampler_cc path (python/lora_receiver.py:58-61) is host plumbing, not built")
         # python/lora_receiver.py:53
         self.decoder = decoder(samp_rate / decimation, bandwidth, sf, implicit, cr, crc, reduced_rate,
                                disable_drift_correction, **decoder_kw)
+        if self.decoder.n_streams != 1:
+            raise ValueError("lora_receiver feeds one channel (channel_list[0]) to one decoder stream, like the reference; "
+                             "use decoder(..., n_streams=N).work_batch for many channels")
         self.frames = self.decoder.frames            # hier-block message port 'frames' (:56,:68)
+        # decoder 'control' -> channelizer 'control' (:64): the ("cfo" . x) message the reference's decoder would publish at
+        # SYNC (lib/decoder_impl.cc:774-776, commented out there) and lib/controller_impl.cc:52-57 turns into apply_cfo(x).
+        # Opt-in here as well: with cfo_feedback the estimates made during a run() retune the channelizer afterwards.
+        self.cfo_feedback = bool(cfo_feedback) and self.channelizer is not None
+        self._cfo_seen = 0
+        if self.cfo_feedback:
+            self.decoder.set_cfo_estimate(True)
 
     def message_port_subscribe(self, handler):
         self.decoder.message_port_subscribe(handler)
@@ -48,8 +61,6 @@ class lora_receiver:
         channel_list[0] reaches the decoder, as in the reference (lib/channelizer_impl.cc:47,56-57)."""
         if self.channelizer is None:
             return self.decoder.run(self._front(samples), stream)
-        if self.conj:
-            raise NotImplementedError("conj=True after the GPU channelizer is not wired (host conjugate needs the samples back)")
         x = np.asarray(samples, dtype=np.complex64)
         x = x[: (x.size // self.decimation) * self.decimation]
         limit = int(self.decoder.cfg.max_items_per_call or (1 << 20))
@@ -64,6 +75,11 @@ class lora_receiver:
             if c == 0:
                 break
             pos_out += c
+        if self.cfo_feedback:
+            cfo, n = self.decoder.last_cfo(0)
+            if n > self._cfo_seen:
+                self._cfo_seen = n
+                self.channelizer.apply_cfo(cfo)      # channelizer_impl::apply_cfo, lib/channelizer_impl.cc:68-71
         return pos_out * self.decimation
 
     def get_sf(self):

@@ -160,6 +160,14 @@ int lora_b200_work_batch_sc16(lora_b200_decoder *d, const void *iq_sc16, float s
                               int host_ptr, size_t *consumed /* [n_streams] */, lora_b200_frame_cb cb, void *user);
 /* current state of a stream (LORA_B200_DETECT ...) */
 int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream);
+/* N4: the CFO estimate the reference computes in experimental_determine_cfo (lib/decoder_impl.cc:730-738:
+ * instantaneous frequency of samples x downchirp at index 256 of the synchronised preamble symbol, in Hz) and would
+ * publish as ("cfo" . x) on its "control" port for the channelizer (:774-776, commented out there; consumer
+ * lib/controller_impl.cc:52-57 -> channelizer_impl::apply_cfo).  Off by default: nothing observable changes.  With it
+ * enabled every SYNC step stores the estimate; _last_cfo returns the latest one and how many there have been, for the
+ * host to forward to lora_b200_channelizer_apply_cfo. */
+int lora_b200_set_cfo_estimate(lora_b200_decoder *d, int enable);
+int lora_b200_last_cfo(lora_b200_decoder *d, uint32_t stream, float *cfo_hz, uint32_t *count);
 /* the reference's std::cout hex lines for the frames delivered by the last work call of this
  * stream (" 04 90 40" + " de ad ... (ascii)\n", decoder_impl.cc:832,872) */
 int lora_b200_stdout_last(lora_b200_decoder *d, uint32_t stream, char *buf, size_t cap);
@@ -184,6 +192,9 @@ int lora_b200_channelizer_taps(const lora_b200_channelizer *c, float *out, size_
 /* channelizer_impl::apply_cfo (lib/channelizer_impl.cc:68-71), driven by the "cfo" control message
  * (lib/controller_impl.cc:52-57) */
 int lora_b200_channelizer_apply_cfo(lora_b200_channelizer *c, uint32_t channel, float cfo);
+/* conj != 0: every output sample is conjugated on its way out -- the blocks.conjugate_cc that lora_receiver(conj=True)
+ * wires between the channelizer and the decoder (python/lora_receiver.py:50,70-75), without a host round trip */
+int lora_b200_channelizer_set_conjugate(lora_b200_channelizer *c, int conj);
 int lora_b200_channelizer_work_dev(lora_b200_channelizer *c, const void *in_dev, size_t n_in, void *out_dev,
                                    size_t out_stride, size_t *n_out, void *cuda_stream);
 /* host entry: uploads `in_host`, filters into an internal device buffer; _output() returns the DEVICE
@@ -191,6 +202,8 @@ int lora_b200_channelizer_work_dev(lora_b200_channelizer *c, const void *in_dev,
  * without a host round trip (lora_b200_work_batch(..., host_ptr = 0)). */
 int lora_b200_channelizer_work_host(lora_b200_channelizer *c, const void *in_host, size_t n_in, size_t *n_out);
 const void *lora_b200_channelizer_output(const lora_b200_channelizer *c, uint32_t channel, size_t *stride_items);
+/* host copy of one channel's output of the last _work_host call (what a GNU Radio block's work() hands downstream) */
+int lora_b200_channelizer_read_output(const lora_b200_channelizer *c, uint32_t channel, void *host_dst, size_t n_items);
 uint64_t lora_b200_channelizer_launch_count(const lora_b200_channelizer *c);
 
 /* how many kernels this library has launched since creation (bench.py's gpu_launches) */

@@ -76,6 +76,8 @@ def lib():
         L.lr_detect_upchirp.argtypes = [vp, vp, vp]
         L.lr_detect_downchirp.restype = f32
         L.lr_detect_downchirp.argtypes = [vp, vp]
+        L.lr_experimental_determine_cfo.restype = f32
+        L.lr_experimental_determine_cfo.argtypes = [vp, vp]
         L.lr_determine_energy.restype = f32
         L.lr_determine_energy.argtypes = [vp, vp]
         L.lr_demod_fft_batch.argtypes = [vp, vp, sz, vp, vp]
@@ -195,6 +197,11 @@ class RefDecoder:
         x = self._iq(x)
         assert x.size >= self.sps
         return float(self.L.lr_detect_downchirp(self.h, _ptr(x)))
+
+    def experimental_determine_cfo(self, x):
+        x = self._iq(x)
+        assert x.size >= self.sps
+        return float(self.L.lr_experimental_determine_cfo(self.h, _ptr(x)))
 
     def energy(self, x):
         x = self._iq(x)

@@ -153,6 +153,9 @@ float lr_detect_upchirp(lr_decoder *d, const lr_cf *samples, int32_t *index) {
     return c;
 }
 float lr_detect_downchirp(lr_decoder *d, const lr_cf *samples) { return d->impl->detect_downchirp(cx(samples), d->impl->d_samples_per_symbol); }
+float lr_experimental_determine_cfo(lr_decoder *d, const lr_cf *samples) {       // :730-738 (its call site :774 is commented out)
+    return d->impl->experimental_determine_cfo(cx(samples), d->impl->d_samples_per_symbol);
+}
 float lr_determine_energy(lr_decoder *d, const lr_cf *samples) { return d->impl->determine_energy(cx(samples)); }
 
 void lr_demod_fft_batch(lr_decoder *d, const lr_cf *iq, size_t n_symbols, uint32_t *bins, float *mags) {

@@ -118,3 +118,97 @@ def test_apply_cfo_retunes(torch):
     f_after = np.angle(np.mean(y[1:] * np.conj(y[:-1]))) * fs / (2 * np.pi)
     assert abs(f_before - 10e3) < 50 and abs(f_after) < 50
     ch.close()
+
+
+def test_receiver_conj_after_channelizer(torch):
+    """lora_receiver(conj=True): channelizer -> conjugate_cc -> decoder (python/lora_receiver.py:62-63,70-75).  A spectrally
+    inverted capture (conjugated IQ, mirrored offset) decodes only with conj=True; the conjugation happens in the
+    channelizer's output stage on the device."""
+    import gr_lora_b200 as G
+    payload = bytes.fromhex("deadbeef700d")
+    f_off = 100e3
+    x = _wideband_capture(payload, 7, 1e6, 1, f_off, 15.0, 5)
+    xi = np.conj(x)                                           # inverted spectrum: the channel now sits at -f_off
+    center = 868.0e6
+    rx = G.lora_receiver(1e6, center, [center - f_off], 125000, 7, False, 4, True, conj=True, quiet=True)
+    rx.run(xi)
+    assert [f[15:].hex() for _, f in rx.frames] == ["049040deadbeef700d"] * 2
+    plain = G.lora_receiver(1e6, center, [center - f_off], 125000, 7, False, 4, True, conj=False, quiet=True)
+    plain.run(xi)
+    assert [f[15:].hex() for _, f in plain.frames] != ["049040deadbeef700d"] * 2
+    # conjugate flag on the raw channelizer: output == conj(output without it)
+    ch = G.channelizer(1e6, center, [center + 50e3, center - 75e3], 125000, 1)
+    n = 4096
+    d_in = torch.from_numpy(x[:n].copy()).cuda()
+    a = torch.zeros((2, n), dtype=torch.complex64, device="cuda")
+    ch.work_dev(d_in, n, a, n)
+    ch2 = G.channelizer(1e6, center, [center + 50e3, center - 75e3], 125000, 1)
+    ch2.set_conjugate(True)
+    b = torch.zeros((2, n), dtype=torch.complex64, device="cuda")
+    ch2.work_dev(d_in, n, b, n)
+    torch.cuda.synchronize()
+    assert torch.equal(b, torch.conj(a).resolve_conj())
+    ch.close(); ch2.close()
+
+
+def test_receiver_rejects_multi_stream_decoder(torch):
+    import gr_lora_b200 as G
+    with pytest.raises(ValueError, match="one decoder stream"):
+        G.lora_receiver(1e6, 868e6, [868.1e6], 125000, 7, False, 4, True, quiet=True, n_streams=4)
+
+
+def test_cpp_channelizer_shim(torch, tmp_path):
+    """The compiled C++ drop-in (gr_lora_b200/host/channelizer_impl.cc: lora::channelizer::make with the reference's
+    signature, include/lora/channelizer.h:49) driven with GNU-Radio-sized buffers: every channel's output equals the float64
+    restatement, history and rotator phase carry across work() calls, apply_cfo retunes channel 0."""
+    import os
+    import subprocess
+    from gr_lora_b200 import build as B
+    import gr_lora_b200 as G
+    exe = B.build_chan_shim()
+    fs, decim, center = 4e6, 4, 868e6
+    offsets = [1.1e6, -700e3, 300e3]
+    rng = np.random.default_rng(3)
+    n_in = 60000
+    x = (rng.standard_normal(n_in) + 1j * rng.standard_normal(n_in)).astype(np.complex64)
+    f_in = tmp_path / "in.cf32"
+    x.tofile(f_in)
+    cmd = [str(exe), str(f_in), str(tmp_path / "out"), str(fs), str(center), "125000", str(decim), "4096"] + [repr(center + f) for f in offsets]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert f"PRODUCED {n_in // decim}" in p.stderr
+    taps = G.channelizer(fs, center, [center], 125000, decim).taps()
+    for c, f in enumerate(offsets):
+        y = np.fromfile(tmp_path / f"out.{c}.cf32", np.complex64)
+        f_eff = float(np.float32(center + f)) - float(np.float32(center))
+        ref = xlating_fir_reference(x, taps, f_eff, fs, decim)
+        assert y.size == ref.size
+        assert np.max(np.abs(y - ref)) / np.max(np.abs(ref)) < 2e-5, c
+    # apply_cfo after the first buffer: channel 0 of the rest is tuned 10 kHz higher
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env={**os.environ, "CHAN_SHIM_CFO": "10000"})
+    assert p.returncode == 0, p.stderr
+    y = np.fromfile(tmp_path / "out.0.cf32", np.complex64)
+    f_eff = float(np.float32(center + offsets[0])) - float(np.float32(center))
+    ref0 = xlating_fir_reference(x, taps, f_eff, fs, decim)
+    assert np.max(np.abs(y[:4096] - ref0[:4096])) / np.max(np.abs(ref0)) < 2e-5
+    assert np.max(np.abs(y[8192:] - ref0[8192:])) / np.max(np.abs(ref0)) > 0.1
+
+
+def test_cfo_feedback_retunes_the_channelizer(torch):
+    """decoder 'control' -> channelizer 'control' (python/lora_receiver.py:64; lib/decoder_impl.cc:774-776 commented out in the
+    reference): with cfo_feedback the estimate of one run() is applied with apply_cfo, the next run sees the residual."""
+    import gr_lora_b200 as G
+    payload = bytes.fromhex("deadbeef700d")
+    f_off, cfo = 100e3, 3000.0
+    x = _wideband_capture(payload, 7, 1e6, 1, f_off + cfo, 25.0, 9)
+    center = 868.0e6
+    rx = G.lora_receiver(1e6, center, [center + f_off], 125000, 7, False, 4, True, quiet=True, cfo_feedback=True)
+    rx.run(x)
+    first, n1 = rx.decoder.last_cfo()
+    assert n1 >= 1 and abs(first - cfo) < 400.0
+    rx.run(x)                                                 # same capture again: the channelizer is now tuned first Hz higher
+    second, n2 = rx.decoder.last_cfo()
+    assert n2 > n1 and abs(second) < 400.0
+    off = G.lora_receiver(1e6, center, [center + f_off], 125000, 7, False, 4, True, quiet=True)
+    off.run(x)
+    assert off.decoder.last_cfo() == (0.0, 0)

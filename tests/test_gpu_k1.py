@@ -101,7 +101,7 @@ def test_k1_full_size_property_config2(torch):
     import gr_lora_b200 as G
     sys_path_bench = __import__("bench")
     dev = torch.device("cuda", 0)
-    iq, vals = sys_path_bench.synth_batch(torch, 7, 256, 256, 10.0, dev, 0x4C6F5202)
+    iq, vals = sys_path_bench.synth_batch(torch, 7, 256 * 256, 10.0, dev, 0x4C6F5202)
     n = iq.shape[0]
     dec = G.decoder(1e6, 125000, 7, False, 4, True, demod="fft", quiet=True)
     bins = torch.empty(n, dtype=torch.int32, device=dev)

@@ -178,3 +178,30 @@ def test_other_sample_rates_gradient_path(torch, oracle, fs):
     dec.close()
     with pytest.raises(RuntimeError, match="samp_rate/bandwidth == 8"):
         G.decoder(fs, 125000, sf, False, cr, True, quiet=True, demod="fft")
+
+
+@pytest.mark.parametrize("cfo_hz", [0.0, 800.0, -2500.0])
+def test_cfo_estimate_equals_reference_function(torch, oracle, ref, cfo_hz):
+    """N4: lora_b200_set_cfo_estimate -> experimental_determine_cfo (lib/decoder_impl.cc:730-738) at the SYNC step, on the
+    window the reference's commented-out call site would pass (&input[i], :774).  Compared with the reference's own
+    function (oracle/_ref); frames and the step trace are untouched by the option."""
+    import gr_lora_b200 as G
+    from conftest import make_capture
+    x = make_capture(bytes.fromhex("0123456789abcdef"), 8, 4, True, seed=33, cfo_hz=cfo_hz)
+    plain = G.decoder(1e6, 125000, 8, False, 4, True, quiet=True, max_items_per_call=x.size, trace_capacity=4096)
+    plain.work(x)
+    dec = G.decoder(1e6, 125000, 8, False, 4, True, quiet=True, max_items_per_call=x.size, trace_capacity=4096)
+    dec.set_cfo_estimate(True)
+    dec.work(x)
+    assert dec.frames == plain.frames and dec.trace() == plain.trace()
+    assert plain.last_cfo() == (0.0, 0)
+    cfo, n = dec.last_cfo()
+    tr = dec.trace()
+    sync_steps = [k for k, s in enumerate(tr) if s[0] == 1]
+    assert n == len(sync_steps) >= 1
+    k = sync_steps[-1]
+    pos = sum(s[1] for s in tr[:k]) + tr[k][1]              # &input[i]: the window start after the SYNC step's consume
+    want = ref.RefDecoder(sf=8).experimental_determine_cfo(x[pos:pos + 2048])
+    assert abs(cfo - want) < 0.5, (cfo, want)
+    assert abs(cfo - cfo_hz) < 150.0                         # a one-sample-pair estimate: noisy, but it is the CFO
+    dec.close(); plain.close()
