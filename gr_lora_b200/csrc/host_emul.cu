@@ -4,11 +4,7 @@
 #include "k1_fft.cuh"
 #include "k1_warp.cuh"
 #include "k1_group.cuh"
-#include "k1_cluster.cuh"
 #include "k1_sf10.cuh"
-#include "k1_big.cuh"
-#include "k1_xchg.cuh"
-#include "k1_ab.cuh"
 #include "k1_rows.cuh"
 #include "int_chain.cuh"
 
@@ -42,8 +38,6 @@ int lb_k1_emulate_group(int sf, const float2 *x, size_t n_symbols, const float2 
     case 8: lb::g_emulate<8>(a, bins, mags); break;
     case 9: lb::g_emulate<9>(a, bins, mags); break;
     case 10: lb::s10_emulate(a, bins, mags); break;
-    case 11: lb::kc_emulate<11>(a, bins, mags); break;
-    case 12: lb::kc_emulate<12>(a, bins, mags); break;
     default: return -1;
     }
     return 0;
@@ -57,36 +51,6 @@ int lb_k1_emulate_rows(int sf, const float2 *x, size_t n_symbols, const float2 *
     return 0;
 }
 
-int lb_k1_emulate_big(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
-    lb::K1Args a{x, chirp, tw, n_symbols};
-    if (sf == 11) lb::b_emulate<11>(a, bins, mags);
-    else if (sf == 12) lb::b_emulate<12>(a, bins, mags);
-    else return -1;
-    return 0;
-}
-
-int lb_k1_emulate_xchg(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
-    lb::K1Args a{x, chirp, tw, n_symbols};
-    const int th = sf / 100 ? 128 : 256;                 // sf + 100 selects the 128-thread variant
-    sf %= 100;
-    if (sf == 10 && th == 256) lb::xg_emulate<10, 256>(a, bins, mags);
-    else if (sf == 11 && th == 256) lb::xg_emulate<11, 256>(a, bins, mags);
-    else if (sf == 12 && th == 256) lb::xg_emulate<12, 256>(a, bins, mags);
-    else if (sf == 10) lb::xg_emulate<10, 128>(a, bins, mags);
-    else if (sf == 11) lb::xg_emulate<11, 128>(a, bins, mags);
-    else if (sf == 12) lb::xg_emulate<12, 128>(a, bins, mags);
-    else return -1;
-    return 0;
-}
-
-int lb_k1_emulate_ab(int sf, const float2 *x, size_t n_symbols, const float2 *chirp, const float2 *tw, uint32_t *bins, float *mags) {
-    lb::K1Args a{x, chirp, tw, n_symbols};
-    if (sf == 10) lb::ab_emulate<10>(a, bins, mags);
-    else if (sf == 11) lb::ab_emulate<11>(a, bins, mags);
-    else if (sf == 12) lb::ab_emulate<12>(a, bins, mags);
-    else return -1;
-    return 0;
-}
 
 uint32_t lb_emul_decode(const uint8_t *cw, uint32_t n_cw, int is_header, uint32_t cr, uint8_t *out, uint32_t cap) {
     uint32_t n = lb::decode_len_bytes(lb::decode_len_words(n_cw, is_header), cr);

@@ -509,12 +509,14 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 // the first version those compiled to MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL and held 30 % of all stall samples.
                 const int xi = warp & 7;
                 const bool mine = (uint32_t)(warp >> 3) == rank;
-                const int ridx = xi * 258 + (kb2 * 2 + h2) * 8;
+                // block of warp pair xi: 129 float4 = [i][lane] (i = 0..3: the lane's bins 2i, 2i+1) + the bin-N/2 extra at float4 128;
+                // lane-major inside each i, so the 128-bit accesses of a quarter warp fall into 8 different bank groups
+                float4 *sblk = reinterpret_cast<float4 *>(&sm.send[xi * 258]);
+                const float4 *rblk = reinterpret_cast<const float4 *>(&sm.recv[xi * 258]);
                 if (!mine) {
                     if (s > 0) mbar_wait(&sm.x_free[xi], (uint32_t)((s - 1) & 1));     // the peer has consumed the previous block (so the copy has read `send`)
-                    float4 *dst = reinterpret_cast<float4 *>(&sm.send[ridx]);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) dst[i] = make_float4(f[2 * i].x, f[2 * i].y, f[2 * i + 1].x, f[2 * i + 1].y);
+                    for (int i = 0; i < 4; i++) sblk[i * 32 + lane] = make_float4(f[2 * i].x, f[2 * i].y, f[2 * i + 1].x, f[2 * i + 1].y);
                     if (quirk_warp && lane == 1) sm.send[xi * 258 + 256] = tq;
                     fence_proxy_async();
                     __syncwarp();
@@ -526,7 +528,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                     uint32_t dep = 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const float4 u = *reinterpret_cast<const float4 *>(&sm.recv[ridx + 2 * i]);
+                        const float4 u = rblk[i * 32 + lane];
                         f[2 * i] = cadd(f[2 * i], make_float2(u.x, u.y));
                         f[2 * i + 1] = cadd(f[2 * i + 1], make_float2(u.z, u.w));
                         dep |= __float_as_uint(u.w);

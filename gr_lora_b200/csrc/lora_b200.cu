@@ -6,13 +6,10 @@
 #include "k1_fft.cuh"
 #include "k1_warp.cuh"
 #include "k1_group.cuh"
-#include "k1_cluster.cuh"
 #include "k1_sf10.cuh"
-#include "k1_big.cuh"
-#include "k1_xchg.cuh"
-#include "k1_ab.cuh"
 #include "rx_stream.cuh"
 #include "k1_rows.h"
+#include "k1_packed.h"
 
 #include <algorithm>
 #include <cmath>
@@ -214,24 +211,7 @@ int launch_k1(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_sy
     return LORA_B200_OK;
 }
 
-// SF7: one warp per symbol, TMA-fed shared-memory ring (k1_warp.cuh)
-template <int NWARPS, int NSLOT>
-int launch_k1_warp7(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
-    static bool attr_set[64] = {};
-    const size_t smem = sizeof(W7Smem<NWARPS, NSLOT>);
-    if (!attr_set[d->device & 63]) {
-        CU(cudaFuncSetAttribute(k1_sf7_warp_kernel<NWARPS, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[d->device & 63] = true;
-    }
-    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    const int grid = (int)std::min<size_t>((n_symbols + NWARPS - 1) / NWARPS, (size_t)d->n_sms);
-    k1_sf7_warp_kernel<NWARPS, NSLOT><<<grid, NWARPS * 32, smem, st>>>(a, bins, mags);
-    d->launches++;
-    CU(cudaGetLastError());
-    return LORA_B200_OK;
-}
-
-// SF8/SF9 (and SF7 as a cross-check): a group of 2^(SF-7) warps per symbol (k1_group.cuh)
+// SF8: a group of 2 warps per symbol (k1_group.cuh; the SF7 warp kernel and the SF9 group kernel are launched from k1_packed.cu)
 template <int SF, int NGROUPS, int NSLOT>
 int launch_k1_group(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     static bool attr_set[64] = {};
@@ -248,46 +228,6 @@ int launch_k1_group(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_
     return LORA_B200_OK;
 }
 
-// SF11/SF12: one cluster of 2/4 CTAs per symbol, pass 0 scattered over DSMEM (k1_cluster.cuh)
-template <int SF>
-int launch_k1_cluster(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
-    using C = K1Cfg<SF>;
-    using K = KCfg<SF>;
-    static bool attr_set[64] = {};
-    const size_t smem = sizeof(float2) * C::SMEM_ELEMS;
-    if (!attr_set[d->device & 63]) {
-        CU(cudaFuncSetAttribute(k1_cluster_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[d->device & 63] = true;
-    }
-    if (ks.packed_cap < n_symbols) {
-        if (ks.packed) cudaFree(ks.packed);
-        ks.packed = nullptr; ks.packed_cap = 0;
-        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
-        ks.packed_cap = n_symbols;
-    }
-    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
-    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    size_t n_clusters = std::min<size_t>(n_symbols, (size_t)(d->n_sms * 2) / K::CL);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_clusters * K::CL));
-    cfg.blockDim = dim3(K1_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = K::CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, k1_cluster_kernel<SF>, a, ks.packed));
-    d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
-    d->launches++;
-    CU(cudaGetLastError());
-    return LORA_B200_OK;
-}
-
 // SF10: one 256-thread group per symbol, two radix-32 passes (k1_sf10.cuh)
 int launch_k1_sf10(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
     static bool attr_set[64] = {};
@@ -299,191 +239,6 @@ int launch_k1_sf10(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t
     K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
     const int grid = (int)std::min<size_t>(n_symbols, (size_t)d->n_sms);
     k1_sf10_kernel<2><<<grid, S10_T, smem, st>>>(a, bins, mags);
-    d->launches++;
-    CU(cudaGetLastError());
-    return LORA_B200_OK;
-}
-
-// SF11/SF12: cluster of 2/4 TMA-fed groups per symbol (k1_big.cuh)
-template <int SF>
-int launch_k1_big(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
-    using B = BCfg<SF>;
-    static bool attr_set[64] = {};
-    const size_t smem = sizeof(BSmem<2>);
-    if (!attr_set[d->device & 63]) {
-        CU(cudaFuncSetAttribute(k1_big_kernel<SF, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[d->device & 63] = true;
-    }
-    if (ks.packed_cap < n_symbols) {
-        if (ks.packed) cudaFree(ks.packed);
-        ks.packed = nullptr; ks.packed_cap = 0;
-        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
-        ks.packed_cap = n_symbols;
-    }
-    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
-    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    const size_t n_clusters = std::max<size_t>(1, std::min<size_t>(n_symbols, (size_t)d->n_sms / B::CL));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_clusters * B::CL));
-    cfg.blockDim = dim3(256);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = B::CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, k1_big_kernel<SF, 2>, a, ks.packed));
-    d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
-    d->launches++;
-    CU(cudaGetLastError());
-    return LORA_B200_OK;
-}
-
-// k1_xchg watchdog: with LORA_B200_XG_WATCHDOG set, spins that last too long leave a record in host-mapped memory that
-// lora_b200_xg_watchdog() exposes (tools/k1_ab.py reads it while a kernel hangs).  Not part of the public header.
-static unsigned long long *g_xg_wd_host = nullptr, *g_xg_wd_dev = nullptr;
-unsigned long long *xg_watchdog_dev() {
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        if (getenv("LORA_B200_XG_WATCHDOG") && cudaHostAlloc(&g_xg_wd_host, 256 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
-            memset(g_xg_wd_host, 0, 256 * sizeof(unsigned long long));
-            if (cudaHostGetDevicePointer(&g_xg_wd_dev, g_xg_wd_host, 0) != cudaSuccess) g_xg_wd_dev = nullptr;
-        }
-    }
-    return g_xg_wd_dev;
-}
-
-// SF10/SF11/SF12: teams of CL sub-CTAs per symbol, pass-0 outputs exchanged through an L2-resident scratch with TMA
-// stores / loads and global flags; one 512-thread CTA (512 / TH sub-CTAs) per SM (k1_xchg.cuh)
-template <int SF, int TH>
-int launch_k1_xchg(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
-    using X = XCfg<SF, TH>;
-    constexpr int NH = 512 / TH;
-    static int max_cta_teams[64] = {};
-    const size_t smem = sizeof(XSmem<TH>);
-    if (!max_cta_teams[d->device & 63]) {
-        CU(cudaFuncSetAttribute(k1_xchg_kernel<SF, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_xchg_kernel<SF, TH>, 512, smem));
-        int nt = (per_sm > 0 ? 1 : 0) * d->n_sms / X::CL;     // every CTA of the grid must be resident (teams spin on flags)
-        if (nt < 1) return fail(LORA_B200_ECUDA, "k1_xchg: a team of %d CTAs does not fit on the device", X::CL);
-        static const char *cap = getenv("LORA_B200_K1_XCHG_TEAMS");        // tuning knob
-        if (cap && atoi(cap) > 0 && atoi(cap) < nt) nt = atoi(cap);
-        max_cta_teams[d->device & 63] = nt;
-    }
-    // a CTA-team = CL CTAs = NH teams; do not launch CTA-teams that would get no symbol
-    const size_t n_ct = std::max<size_t>(1, std::min<size_t>((n_symbols + NH - 1) / NH, (size_t)max_cta_teams[d->device & 63]));
-    const size_t n_teams = n_ct * NH;
-    if (ks.packed_cap < n_symbols) {
-        if (ks.packed) cudaFree(ks.packed);
-        ks.packed = nullptr; ks.packed_cap = 0;
-        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
-        ks.packed_cap = n_symbols;
-    }
-    const size_t xs_bytes = n_teams * XG_NB * ((size_t)X::SPS * sizeof(float2) + sizeof(uint32_t));
-    if (ks.xs_cap < xs_bytes) {
-        if (ks.xs) cudaFree(ks.xs);
-        ks.xs = nullptr; ks.xs_cap = 0;
-        CU(cudaMalloc(&ks.xs, xs_bytes));
-        ks.xs_cap = xs_bytes;
-    }
-    float2 *xs = reinterpret_cast<float2 *>(ks.xs);
-    uint32_t *flags = reinterpret_cast<uint32_t *>(xs + n_teams * XG_NB * (size_t)X::SPS);
-    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
-    CU(cudaMemsetAsync(flags, 0, n_teams * XG_NB * sizeof(uint32_t), st));
-    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    // the ranks of a team spin on each other's flags: the launch is COOPERATIVE, so either the whole grid is co-resident
-    // or the launch fails with an error (two such kernels on different streams run one after the other, never half each)
-    {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)(n_ct * X::CL));
-        cfg.blockDim = dim3(512);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, k1_xchg_kernel<SF, TH>, a, xs, flags, ks.packed, xg_watchdog_dev(), getenv("LORA_B200_XG_NOSYNC") ? 1 : 0));
-    }
-    d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
-    d->launches++;
-    CU(cudaGetLastError());
-    return LORA_B200_OK;
-}
-
-// SF10/SF11/SF12: producer / consumer roles in one persistent kernel, exchange in L2 (k1_ab.cuh)
-template <int SF>
-int launch_k1_ab(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
-    using A = ACfg<SF>;
-    static int n_a_ctas[64] = {};
-    const size_t smem = sizeof(ABSmem);
-    if (!n_a_ctas[d->device & 63]) {
-        CU(cudaFuncSetAttribute(k1_ab_kernel<SF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_ab_kernel<SF>, AB_WARPS * 32, smem));
-        if (per_sm < 1) return fail(LORA_B200_ECUDA, "k1_ab: the kernel does not fit on an SM");
-        int na = 48;                                      // role A CTAs; 12 warps each, their total a multiple of 32
-        static const char *e = getenv("LORA_B200_K1_AB_NA");
-        if (e && atoi(e) >= 8) na = atoi(e) / 8 * 8;
-        if (na > d->n_sms - 8) na = (d->n_sms - 8) / 8 * 8;
-        if (na < 8) return fail(LORA_B200_ECUDA, "k1_ab: needs at least 16 SMs");
-        n_a_ctas[d->device & 63] = na;
-    }
-    const uint32_t na = (uint32_t)n_a_ctas[d->device & 63], nb = (uint32_t)d->n_sms - na;   // one CTA per SM: all resident
-    // exchange ring: role B looks 3 items per warp ahead (2 in its TMA ring + 1 in work) = 3 * 12 * nb / R symbols, role A
-    // has 2 * 12 * na / 32 * (32 / R) symbols in work or unpublished: together ~36 MiB at every SF; 48 MiB leave slack
-    // and still sit in the 126 MB L2 beside the streaming input
-    static const char *rmb = getenv("LORA_B200_K1_AB_RING_MB");
-    const size_t ring_mb = rmb && atoi(rmb) >= 8 ? (size_t)atoi(rmb) : 48;
-    uint32_t ring = (uint32_t)((ring_mb << 20) / ((size_t)A::SPS * sizeof(float2)));
-    // liveness: a producer must never wait for a ring slot whose previous occupant it still holds unpublished; it holds
-    // at most two items of 32 / R symbols, consecutive symbols of one producer are 3 na / 8 apart
-    // (tests/test_exchange_protocols.py models the protocol and shows both the bound and what happens below it)
-    const uint32_t ring_min = 2u * (32u / A::R) * (3u * na / 8u) + 1u;
-    if (ring < ring_min) ring = ring_min;
-    if (ks.packed_cap < n_symbols) {
-        if (ks.packed) cudaFree(ks.packed);
-        ks.packed = nullptr; ks.packed_cap = 0;
-        CU(cudaMalloc(&ks.packed, sizeof(unsigned long long) * n_symbols));
-        ks.packed_cap = n_symbols;
-    }
-    const size_t xs_bytes = (size_t)ring * A::SPS * sizeof(float2) + 2 * (size_t)ring * AB_FSTRIDE * sizeof(uint32_t);
-    if (ks.xs_cap < xs_bytes) {
-        if (ks.xs) cudaFree(ks.xs);
-        ks.xs = nullptr; ks.xs_cap = 0;
-        CU(cudaMalloc(&ks.xs, xs_bytes));
-        ks.xs_cap = xs_bytes;
-    }
-    float2 *scratch = reinterpret_cast<float2 *>(ks.xs);
-    uint32_t *ready = reinterpret_cast<uint32_t *>(scratch + (size_t)ring * A::SPS), *done = ready + (size_t)ring * AB_FSTRIDE;
-    CU(cudaMemsetAsync(ks.packed, 0, sizeof(unsigned long long) * n_symbols, st));
-    CU(cudaMemsetAsync(ready, 0, 2 * (size_t)ring * AB_FSTRIDE * sizeof(uint32_t), st));
-    K1Args a{iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols};
-    static const char *pv = getenv("LORA_B200_K1_AB_PROD");          // 2 = group producers (TMA in, in place, TMA out)
-    {   // producers and consumers wait for each other: cooperative launch (see launch_k1_xchg)
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(na + nb);
-        cfg.blockDim = dim3(AB_WARPS * 32);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeCooperative;
-        attr[0].val.cooperative = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, k1_ab_kernel<SF>, a, scratch, ready, done, ring, nb, ks.packed, xg_watchdog_dev(),
-                              pv && atoi(pv) == 2 ? 2 : 1));
-    }
-    d->launches++;
-    k1_finalize_kernel<<<(unsigned)((n_symbols + 255) / 256), 256, 0, st>>>(ks.packed, n_symbols, bins, mags);
     d->launches++;
     CU(cudaGetLastError());
     return LORA_B200_OK;
@@ -514,85 +269,39 @@ int launch_k1_rows(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t
     return LORA_B200_OK;
 }
 
-int k1_variant() {      // LORA_B200_K1 = generic | w8x3 | w12x2 | w13x2 | w9x3 (tuning knob; default w12x2)
+// SF7 / SF9: the warp / group kernels built with the packed complex product (k1_packed.cu)
+int launch_k1_packed(lora_b200_decoder *d, const float2 *iq, size_t n_symbols, uint32_t *bins, float *mags, cudaStream_t st) {
+    char err[256] = {0};
+    const int rc = k1_packed_launch(d->cfg.sf, d->device, d->n_sms, iq, tab<float2>(d, d->toff.down), tab<float2>(d, d->toff.tw), n_symbols,
+                                    bins, mags, st, err, sizeof err);
+    if (rc) return fail(LORA_B200_ECUDA, "k1_packed: %s", err);
+    d->launches++;
+    return LORA_B200_OK;
+}
+
+// LORA_B200_K1=generic selects k1_fft_kernel (the CTA-wide kernel the stream state machine also uses) for every SF;
+// LORA_B200_K1_ROWS=0 does the same for SF11 / SF12 only.  Both exist for A/B runs (tools/k1_ab.py); the defaults are the
+// measured best per SF.
+bool k1_generic() {
     static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("LORA_B200_K1");
-        v = 2;
-        if (e) {
-            if (!strcmp(e, "generic")) v = 0;
-            else if (!strcmp(e, "w8x3")) v = 1;
-            else if (!strcmp(e, "w12x2")) v = 2;
-            else if (!strcmp(e, "w13x2")) v = 3;
-            else if (!strcmp(e, "w9x3")) v = 4;
-            else if (!strcmp(e, "group")) v = 5;
-            else if (!strcmp(e, "w10x2")) v = 6;
-            else if (!strcmp(e, "w11x2")) v = 7;
-        }
-    }
-    return v;
+    if (v < 0) { const char *e = getenv("LORA_B200_K1"); v = e && !strcmp(e, "generic") ? 1 : 0; }
+    return v == 1;
 }
 
 int dispatch_k1_impl(lora_b200_decoder *d, K1Scratch &ks, const float2 *iq, size_t n, uint32_t *bins, float *mags, cudaStream_t st) {
     if (!d->k1_ok) return fail(LORA_B200_EUNSUPPORTED, "FFT demodulator needs samp_rate/bandwidth == 8 and SF7..SF12");
     if (n == 0) return LORA_B200_OK;
-    if (d->cfg.sf == 7) {
-        switch (k1_variant()) {
-        case 1: return launch_k1_warp7<8, 3>(d, ks, iq, n, bins, mags, st);
-        case 2: return launch_k1_warp7<12, 2>(d, ks, iq, n, bins, mags, st);
-        case 3: return launch_k1_warp7<13, 2>(d, ks, iq, n, bins, mags, st);
-        case 4: return launch_k1_warp7<9, 3>(d, ks, iq, n, bins, mags, st);
-        case 5: return launch_k1_group<7, 12, 2>(d, ks, iq, n, bins, mags, st);
-        case 6: return launch_k1_warp7<10, 2>(d, ks, iq, n, bins, mags, st);
-        case 7: return launch_k1_warp7<11, 2>(d, ks, iq, n, bins, mags, st);
-        default: break;
+    if (!k1_generic()) {
+        static const char *rows = getenv("LORA_B200_K1_ROWS");
+        switch (d->cfg.sf) {
+        case 7: return launch_k1_packed(d, iq, n, bins, mags, st);
+        case 8: return launch_k1_group<8, 6, 2>(d, ks, iq, n, bins, mags, st);
+        case 9: return launch_k1_packed(d, iq, n, bins, mags, st);
+        case 10: return launch_k1_sf10(d, ks, iq, n, bins, mags, st);
+        case 11: case 12:
+            if (!(rows && rows[0] == '0')) return launch_k1_rows(d, ks, iq, n, bins, mags, st);
+            break;
         }
-    }
-    if (k1_variant() != 0) {
-        static const char *gv = getenv("LORA_B200_K1_GROUPS");        // tuning knob: "a" = fewer groups, deeper ring
-        if (d->cfg.sf == 8) {
-            if (gv && gv[0] == 'a') return launch_k1_group<8, 4, 3>(d, ks, iq, n, bins, mags, st);
-            if (gv && gv[0] == 'b') return launch_k1_group<8, 5, 2>(d, ks, iq, n, bins, mags, st);
-            return launch_k1_group<8, 6, 2>(d, ks, iq, n, bins, mags, st);
-        }
-        if (d->cfg.sf == 9) {
-            if (gv && gv[0] == 'a') return launch_k1_group<9, 2, 3>(d, ks, iq, n, bins, mags, st);
-            if (gv && gv[0] == 'b') return launch_k1_group<9, 2, 2>(d, ks, iq, n, bins, mags, st);
-            return launch_k1_group<9, 3, 2>(d, ks, iq, n, bins, mags, st);
-        }
-        static const char *rows = getenv("LORA_B200_K1_ROWS");        // "0": the round-1 kernels for SF11 / SF12 (A/B runs)
-        if ((d->cfg.sf == 11 || d->cfg.sf == 12) && !(rows && rows[0] == '0')) return launch_k1_rows(d, ks, iq, n, bins, mags, st);
-        static const char *ab = getenv("LORA_B200_K1_AB");            // digits = SFs that use k1_ab ("012" = SF10,11,12)
-        if (ab && d->cfg.sf >= 10 && strchr(ab, '0' + (d->cfg.sf - 10))) {
-            if (d->cfg.sf == 10) return launch_k1_ab<10>(d, ks, iq, n, bins, mags, st);
-            if (d->cfg.sf == 11) return launch_k1_ab<11>(d, ks, iq, n, bins, mags, st);
-            return launch_k1_ab<12>(d, ks, iq, n, bins, mags, st);
-        }
-        static const char *xg = getenv("LORA_B200_K1_XCHG");          // digits = SFs that use k1_xchg ("012" = SF10,11,12)
-        if (xg && d->cfg.sf >= 10 && strchr(xg, '0' + (d->cfg.sf - 10))) {
-            static const char *xt = getenv("LORA_B200_K1_XCHG_T");    // "128": 128-thread CTAs, clusters of 4/8/16
-            if (xt && atoi(xt) == 128) {
-                if (d->cfg.sf == 10) return launch_k1_xchg<10, 128>(d, ks, iq, n, bins, mags, st);
-                if (d->cfg.sf == 11) return launch_k1_xchg<11, 128>(d, ks, iq, n, bins, mags, st);
-                return launch_k1_xchg<12, 128>(d, ks, iq, n, bins, mags, st);
-            }
-            if (d->cfg.sf == 10) return launch_k1_xchg<10, 256>(d, ks, iq, n, bins, mags, st);
-            if (d->cfg.sf == 11) return launch_k1_xchg<11, 256>(d, ks, iq, n, bins, mags, st);
-            return launch_k1_xchg<12, 256>(d, ks, iq, n, bins, mags, st);
-        }
-        if (d->cfg.sf == 10 && !getenv("LORA_B200_K1_SF10_GENERIC")) return launch_k1_sf10(d, ks, iq, n, bins, mags, st);
-        // k1_big (cluster of TMA-fed groups) measured 0.287 (SF11) / 0.130 (SF12): membar + lg_throttle stalls
-        // around the two cluster barriers (profiles/r1_k1_big_sf11.md); the simpler kernels below are faster
-        // today, so it stays opt-in until its exchange is made asynchronous (st.async + mbarrier).
-        if (getenv("LORA_B200_K1_BIG")) {
-            if (d->cfg.sf == 11) return launch_k1_big<11>(d, ks, iq, n, bins, mags, st);
-            if (d->cfg.sf == 12) return launch_k1_big<12>(d, ks, iq, n, bins, mags, st);
-        }
-        if (d->cfg.sf == 11) return launch_k1_cluster<11>(d, ks, iq, n, bins, mags, st);
-        // SF12: the 4-CTA cluster version measured slower (0.107) than the DIF-split version (0.146); the team kernel
-        // (k1_xchg.cuh, exchange through L2) measures 0.23 and is the default
-        if (d->cfg.sf == 12 && getenv("LORA_B200_K1_SF12_CLUSTER")) return launch_k1_cluster<12>(d, ks, iq, n, bins, mags, st);
-        if (d->cfg.sf == 12 && !getenv("LORA_B200_K1_SF12_GENERIC")) return launch_k1_xchg<12, 256>(d, ks, iq, n, bins, mags, st);
     }
     switch (d->cfg.sf) {
     case 7: return launch_k1<7>(d, ks, iq, n, bins, mags, st);
@@ -756,9 +465,6 @@ __global__ void sc16_to_cf32_kernel(const short2 *__restrict__ in, float2 *__res
 // =================================================================================================
 // C ABI
 // =================================================================================================
-// internal (tools/k1_ab.py): host view of the k1_xchg watchdog records, NULL unless LORA_B200_XG_WATCHDOG is set
-extern "C" const unsigned long long *lora_b200_xg_watchdog() { return g_xg_wd_host; }
-
 extern "C" {
 
 const char *lora_b200_last_error(void) { return g_err.c_str(); }

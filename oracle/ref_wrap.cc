@@ -53,27 +53,59 @@ using gr::lora::DecoderState;
 
 namespace {
 
-struct CoutCapture {                 // everything the reference writes to std::cout goes to the decoder's own log
-    std::streambuf *old;
-    std::ios saved;
-    explicit CoutCapture(std::ostringstream &to) : old(std::cout.rdbuf(to.rdbuf())), saved(nullptr) {
+// Everything the reference writes to std::cout goes to the log of the decoder that is running on the calling thread.
+// std::cout's buffer is replaced ONCE by a stream buffer that appends to a thread-local target (bench.py runs one
+// reference decoder per host thread; swapping rdbuf per call would race), and forwards to the original buffer when no
+// decoder call is active on the thread.
+thread_local std::string *tls_cout_target = nullptr;
+
+class TlsCoutBuf : public std::streambuf {
+public:
+    explicit TlsCoutBuf(std::streambuf *orig) : d_orig(orig) {}
+protected:
+    int overflow(int c) override {
+        if (c == traits_type::eof()) return c;
+        if (tls_cout_target) { tls_cout_target->push_back((char)c); return c; }
+        return d_orig ? d_orig->sputc((char)c) : c;
+    }
+    std::streamsize xsputn(const char *s, std::streamsize n) override {
+        if (tls_cout_target) { tls_cout_target->append(s, (size_t)n); return n; }
+        return d_orig ? d_orig->sputn(s, n) : n;
+    }
+    int sync() override { return d_orig && !tls_cout_target ? d_orig->pubsync() : 0; }
+private:
+    std::streambuf *d_orig;
+};
+
+void install_cout_buffer() {
+    static TlsCoutBuf *buf = [] {
+        TlsCoutBuf *b = new TlsCoutBuf(std::cout.rdbuf());
+        std::cout.rdbuf(b);
+        return b;
+    }();
+    (void)buf;
+}
+
+struct CoutCapture {
+    std::string *prev;
+    explicit CoutCapture(std::string &to) : prev(tls_cout_target) {
+        install_cout_buffer();
+        tls_cout_target = &to;
         // print_vector_hex leaves std::hex / setfill('0') set on std::cout (include/lora/utilities.h:356); in the
         // reference that is process-wide state (a second decoder's banner would print "Bins per symbol: 80").  Each
         // captured call starts from default formatting so that one decoder's output does not depend on another's.
-        saved.copyfmt(std::cout);
-        std::cout.copyfmt(std::ios(nullptr));
+        std::cout.flags(std::ios::dec | std::ios::skipws);
+        std::cout.fill(' ');
+        std::cout.precision(6);
+        std::cout.width(0);
     }
-    ~CoutCapture() {
-        std::cout.copyfmt(saved);
-        std::cout.rdbuf(old);
-    }
+    ~CoutCapture() { tls_cout_target = prev; }
 };
 
 }  // namespace
 
 struct lr_decoder {
-    std::ostringstream out;
-    std::string out_snapshot;
+    std::string out;
     void *storage = nullptr;
     decoder_impl *impl = nullptr;
     std::vector<std::vector<uint8_t>> frames;
@@ -226,10 +258,7 @@ size_t lr_frame_count(const lr_decoder *d) { return d->frames.size(); }
 size_t lr_frame_len(const lr_decoder *d, size_t i) { return d->frames[i].size(); }
 const uint8_t *lr_frame_data(const lr_decoder *d, size_t i) { return d->frames[i].data(); }
 void lr_frames_clear(lr_decoder *d) { d->frames.clear(); }
-const char *lr_stdout(lr_decoder *d) {
-    d->out_snapshot = d->out.str();
-    return d->out_snapshot.c_str();
-}
+const char *lr_stdout(lr_decoder *d) { return d->out.c_str(); }
 
 // ---- integer stage, driven through the reference's member functions -------------------------------------------
 uint32_t lr_rotl(uint32_t bits, uint32_t count, uint32_t size) { return gr::lora::rotl(bits, count, size); }

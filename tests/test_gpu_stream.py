@@ -203,5 +203,8 @@ def test_cfo_estimate_equals_reference_function(torch, oracle, ref, cfo_hz):
     pos = sum(s[1] for s in tr[:k]) + tr[k][1]              # &input[i]: the window start after the SYNC step's consume
     want = ref.RefDecoder(sf=8).experimental_determine_cfo(x[pos:pos + 2048])
     assert abs(cfo - want) < 0.5, (cfo, want)
-    assert abs(cfo - cfo_hz) < 150.0                         # a one-sample-pair estimate: noisy, but it is the CFO
+    # what the number means: a chirp cannot tell a frequency offset from a time shift (61 Hz per sample at SF8) and the window
+    # starts where the SYNC correlator put it, so the value is CFO + 61 Hz x (residual misalignment in samples): the
+    # reference marks the function experimental and leaves its call commented out.  The claim here is only that the
+    # device computes the reference's number.
     dec.close(); plain.close()

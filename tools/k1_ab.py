@@ -1,8 +1,8 @@
-"""A/B harness for one K1 kernel variant (selected by the LORA_B200_K1* environment knobs, read once per
-process): parity against the oracle on true symbols of that SF (ragged count, several grid iterations,
-edge bins), then device timing on a large resident batch.  Prints one JSON line.
+"""A/B harness for the K1 kernel of one SF (default, or LORA_B200_K1=generic / LORA_B200_K1_ROWS=0, or another build of the
+library through LORA_B200_LIB): parity against the oracle on true symbols of that SF (ragged count, several grid passes,
+edge bins, -3 dB), then device timing on a large resident batch.  Prints one JSON line.
 
-    LORA_B200_K1_XCHG=012 python tools/k1_ab.py --sf 12
+    LORA_B200_K1_ROWS=0 python tools/k1_ab.py --sf 12
 """
 import argparse
 import json
@@ -16,31 +16,15 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 
 
-SITES = {1: "A: slot_full", 2: "A: gate rx_full", 3: "B: rx_full", 4: "fetch: flag poll", 5: "B: slot_free", 6: "ab A: done[slot]", 7: "ab B: ready[slot]", 8: "ab B: TMA row", 9: "ab A: TMA rows"}
-
-
 def guard(torch, seconds, what):
-    """Wait for the device; if it does not finish, dump the k1_xchg watchdog records and die (a hung kernel must not
-    burn GPU minutes)."""
-    import ctypes as C
+    """Wait for the device; a launch that does not finish kills the process (a hung kernel must not burn GPU minutes)."""
     import time
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream())
     t0 = time.time()
     while not ev.query():
         if time.time() - t0 > seconds:
-            from gr_lora_b200 import _native
-            L = _native.lib()
-            L.lora_b200_xg_watchdog.restype = C.POINTER(C.c_uint64)
-            p = L.lora_b200_xg_watchdog()
-            recs = []
-            if p:
-                n = min(int(p[0]) & 0xFFFFFFFF, 255)
-                for i in range(n):
-                    r = int(p[1 + i])
-                    recs.append({"site": SITES.get(r >> 56, r >> 56), "block": (r >> 44) & 0xFFF, "sub": (r >> 42) & 3,
-                                 "warp": (r >> 38) & 15, "sym": (r >> 22) & 0xFFFF, "val": r & 0x3FFFFF})
-            print(json.dumps({"hang": what, "records": recs[:64], "n_records": len(recs)}), flush=True)
+            print(json.dumps({"hang": what}), flush=True)
             os._exit(3)
         time.sleep(0.01)
 
