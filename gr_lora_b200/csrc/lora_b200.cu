@@ -8,6 +8,7 @@
 #include "k1_group.cuh"
 #include "k1_sf10.cuh"
 #include "rx_stream.cuh"
+#include "rx_warp.cuh"
 #include "k1_rows.h"
 #include "k1_packed.h"
 
@@ -102,7 +103,7 @@ struct lora_b200_decoder {
     float2 *h_stage = nullptr;            // pinned, same shape
     size_t stage_cap = 0;                 // items
     std::vector<unsigned long long> h_consumed;
-    std::vector<RxFrameOut> h_frames;
+    std::vector<RxFrameOut> h_frames, h_sorted;
     std::vector<std::string> stdout_last;
     uint64_t launches = 0;
     bool cfo_estimate = false;            // lora_b200_set_cfo_estimate
@@ -344,8 +345,26 @@ int launch_rx_t(lora_b200_decoder *d, const RxParams &p, int grid, cudaStream_t 
     return LORA_B200_OK;
 }
 
+// SF7 at fs / bw = 8: one warp per stream (rx_warp.cuh); LORA_B200_RX=cta keeps the CTA-per-stream kernel (A/B runs)
+template <bool FFT>
+int launch_rx_warp(lora_b200_decoder *d, const RxParams &p, int n_streams, cudaStream_t st) {
+    static bool attr_set[64] = {};
+    const size_t smem = sizeof(RWSmem);
+    if (!attr_set[d->device & 63]) {
+        CU(cudaFuncSetAttribute(rx_warp_kernel<FFT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[d->device & 63] = true;
+    }
+    rx_warp_kernel<FFT><<<(n_streams + RW_WARPS - 1) / RW_WARPS, RW_WARPS * 32, smem, st>>>(p);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
 int launch_rx(lora_b200_decoder *d, const RxParams &p, int grid, cudaStream_t st) {
     const bool fft = d->cfg.demod == LORA_B200_DEMOD_FFT;
+    static const char *rxk = getenv("LORA_B200_RX");
+    if (d->cfg.sf == 7 && d->sps == (uint32_t)RW_SPS && d->n_bins == (uint32_t)RW_N && !(rxk && !strcmp(rxk, "cta")))
+        return fft ? launch_rx_warp<true>(d, p, grid, st) : launch_rx_warp<false>(d, p, grid, st);
     if (!fft) return launch_rx_t<7, false>(d, p, grid, st);       // SF is a run-time value on the gradient path
     switch (d->cfg.sf) {
     case 7: return launch_rx_t<7, true>(d, p, grid, st);
@@ -379,7 +398,7 @@ int rx_begin(lora_b200_decoder *d) {
 int rx_launch(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t n_items, uint32_t stream_base, uint32_t n_launch) {
     RxParams p;
     memset(&p, 0, sizeof p);
-    p.iq = d_iq; p.stride_items = stride_items; p.n_items = n_items; p.stream_base = stream_base;
+    p.iq = d_iq; p.stride_items = stride_items; p.n_items = n_items; p.stream_base = stream_base; p.n_launch = n_launch;
     p.down = tab<float2>(d, d->toff.down);
     p.down_ifreq = tab<float>(d, d->toff.down_ifreq);
     p.up_ifreq = tab<float>(d, d->toff.up_ifreq);
@@ -425,8 +444,10 @@ int rx_finish(lora_b200_decoder *d, uint32_t stream_base, uint32_t n_launch, siz
         const RxFrameOut &x = d->h_frames[a], &y = d->h_frames[b];
         return x.stream != y.stream ? x.stream < y.stream : x.seq < y.seq;
     });
-    for (uint32_t i : order) {
-        const RxFrameOut &f = d->h_frames[i];
+    d->h_sorted.resize(n_frames);
+    for (uint32_t k = 0; k < n_frames; k++) {
+        const RxFrameOut &f = d->h_frames[order[k]];
+        d->h_sorted[k] = f;
         std::string &so = d->stdout_last[f.stream];
         if (f.n_hdr_print) append_hex(so, f.hdr_print, f.n_hdr_print, false, false);    // :832
         append_hex(so, f.bytes + 18, f.len - 18, true, true);                           // :872
@@ -813,7 +834,9 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
     int rc = ensure_stage(d, n_items * ns, false, sc16);
     if (rc) return rc;
     if (!d->copy_streams[0]) CU(cudaStreamCreateWithFlags(&d->copy_streams[0], cudaStreamNonBlocking));
-    const uint32_t n_groups = std::min<uint32_t>(ns, 8u), gs = (ns + n_groups - 1) / n_groups;
+    // groups: as many as keep every launch at least two CTAs per SM wide (a group is one launch; small batches stay whole)
+    const uint32_t n_groups = std::max<uint32_t>(1u, std::min<uint32_t>(8u, ns / (2u * (uint32_t)d->n_sms)));
+    const uint32_t gs = (ns + n_groups - 1) / n_groups;
     if (d->stage_events.size() < n_groups) {
         const size_t have = d->stage_events.size();
         d->stage_events.resize(n_groups, nullptr);
@@ -857,6 +880,14 @@ int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream) {
     int32_t st = 0;
     CU(cudaMemcpy(&st, &d->d_states[stream].state, sizeof st, cudaMemcpyDeviceToHost));
     return st;
+}
+
+static_assert(sizeof(lora_b200_frame) == sizeof(RxFrameOut) && LORA_B200_MAX_FRAME_BYTES == LB_MAX_FRAME + 2, "public frame record == K8 output record");
+
+size_t lora_b200_frames_last(lora_b200_decoder *d, const lora_b200_frame **frames) {
+    if (!d || !frames) { fail(LORA_B200_EINVAL, "null argument"); return 0; }
+    *frames = reinterpret_cast<const lora_b200_frame *>(d->h_sorted.data());
+    return d->h_sorted.size();
 }
 
 int lora_b200_set_cfo_estimate(lora_b200_decoder *d, int enable) {

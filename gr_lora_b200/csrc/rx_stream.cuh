@@ -70,6 +70,7 @@ struct RxParams {
     size_t stride_items;
     size_t n_items;
     uint32_t stream_base;
+    uint32_t n_launch;                 // streams of this launch (rx_warp_kernel packs several per CTA)
     // tables
     const float2 *down;
     const float *down_ifreq, *up_ifreq, *up_ifreq_v;

@@ -1,0 +1,415 @@
+// rx_warp.cuh -- the receive state machine for SF7 at fs / bw = 8 (sps = 1024), ONE WARP PER STREAM.
+//
+// rx_stream_kernel (rx_stream.cuh) spends a 256-thread CTA on one stream: ~2 100 instructions per thread and symbol window,
+// 16 CTA barriers and several dependent global round trips per step (ncu, profiles/r2_rx_sf7_cta.txt: issue slots 42 %
+// active, stalls wait / barrier / long scoreboard 19 % each; 8.1e6 windows/s on 4096 streams).  At SF7 a window is 1024
+// samples = 32 per lane, which is exactly the shape of the SF7 K1 warp kernel (k1_warp.cuh).  Here a warp owns a stream:
+//   * the window (<= 2 sps samples, 16 KiB), its instantaneous frequency (8 KiB) and the decoder_impl members
+//     (RxStreamState) live in the warp's own shared memory; the four tables (down-chirp, up / down ifreq, 3 x up ifreq)
+//     are shared by the CTA's 7 warps; nothing but the IQ itself is read from global memory inside the loop;
+//   * every step of work() (lib/decoder_impl.cc:740-903) is warp wide with __syncwarp() only: detect_preamble_autocorr,
+//     sliding_norm_cross_correlate_upchirp, detect_downchirp, fine_sync, max_frequency_gradient_idx, determine_energy;
+//     the FFT demodulator is the k1_warp.cuh pipeline on the window in place;
+//   * the sliding correlation of the SYNC step (:399-413), sps lags x (sps - 1) products, keeps 32 lags per lane in
+//     registers and adds the products of every lag IN INDEX ORDER with separate multiply and add -- the order of the
+//     reference's scalar dot product -- so the chosen index is the oracle's bit for bit (the CTA kernel's tree sum may pick
+//     the neighbouring sample on ties); the three-lag fine_sync keeps the CTA kernel's lane-strided order.
+// Same observable behaviour as rx_stream_kernel: frames, consume amounts, per-step trace.  Other SFs and sample rates use
+// rx_stream_kernel.
+#pragma once
+#include "rx_stream.cuh"
+#include "k1_warp.cuh"
+
+namespace lb {
+
+constexpr int RW_SPS = 1024, RW_N = 128, RW_WARPS = 7;
+
+#ifdef __CUDACC__
+struct RWWarp {
+    float4 win[RW_SPS];               // 2 * sps samples (float2) of the current step
+    float ifq[2 * RW_SPS];            // instantaneous frequency of the window; [sps, sps + N) doubles as the bin averages
+    RxStreamState st;
+};
+struct RWSmem {
+    float4 chirp[RW_SPS / 2];         // down-chirp, natural order
+    float up_ifreq[RW_SPS];
+    float down_ifreq[RW_SPS];
+    float up_ifreq_v[3 * RW_SPS];
+    RWWarp w[RW_WARPS];
+};
+
+// window samples [0, n) of the stream into the warp's buffer (8-byte accesses: the window starts at any sample)
+LB_D void rw_load(const float2 *__restrict__ g, float2 *win, int n, int lane) {
+#pragma unroll 8
+    for (int k = lane; k < n; k += 32) win[k] = __ldcs(g + k);
+}
+
+// A3 instantaneous_frequency (:224-244) of win[0, w) into out[0, w); one atan2f per sample
+LB_D void rw_ifreq(const float2 *win, float *out, int w, int lane) {
+    float a_cur;
+    { const float2 s = win[lane]; a_cur = atan2f(s.y, s.x); }
+    for (int base = 0; base < w; base += 32) {
+        const int nb = base + 32 + lane;
+        float a_nxt = 0.0f;
+        if (nb < w) { const float2 s = win[nb]; a_nxt = atan2f(s.y, s.x); }
+        const float n1 = __shfl_sync(0xffffffffu, a_cur, (lane + 1) & 31);
+        const float n2 = __shfl_sync(0xffffffffu, a_nxt, 0);
+        const int j = base + lane;                      // out[j] = wrap(arg x[j+1] - arg x[j])
+        if (j < w - 1) {
+            const float p1 = a_cur;
+            float p2 = lane == 31 ? n2 : n1;
+            // :236-237, float difference against the double M_PI, correction in double
+            while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
+            while ((double)(p2 - p1) < -3.14159265358979323846) p2 = (float)((double)p2 + 6.283185307179586);
+            out[j] = p2 - p1;
+        }
+        a_cur = a_nxt;
+    }
+    __syncwarp();
+    if (lane == 0) out[w - 1] = out[w - 2];
+    __syncwarp();
+}
+
+// A6 fine_sync (:300-338) on ifq[0, sps): lane-strided products + butterfly sum per lag, as fine_sync_block does
+LB_D int rw_fine_sync(const float *ifq, const float *up_v, int bin_idx, int search, int lane) {
+    const int shift_ref = (bin_idx + 1) * 8;                      // :301, decim = 8
+    const int last = 3 * RW_SPS - 1;
+    unsigned long long best = 0ull;
+    for (int li = 0; li < 2 * search - 1; li++) {
+        const int start = shift_ref + (li - (search - 1)) + RW_SPS;   // :310
+        float c = 0.0f;
+#pragma unroll 8
+        for (int k = lane; k < RW_SPS; k += 32) {
+            int idx = start + k;
+            idx = idx < 0 ? 0 : (idx > last ? last : idx);        // defined over-read (oracle D1)
+            c = fmaf(ifq[k], up_v[idx], c);
+        }
+        c = warp_sum(c);
+        const unsigned long long key = corr_key(c, (uint32_t)li);
+        best = key > best ? key : best;
+    }
+    const int lag = best ? (int)key_idx(best) - (search - 1) : 0;
+    return -lag;                                                  // :321
+}
+
+template <bool FFT>
+__global__ void __launch_bounds__(RW_WARPS * 32, 1)
+rx_warp_kernel(RxParams p) {
+    extern __shared__ __align__(128) unsigned char rw_raw[];
+    RWSmem &sm = *reinterpret_cast<RWSmem *>(rw_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int sps = RW_SPS, N = RW_N;
+
+    for (int i = threadIdx.x; i < RW_SPS / 2; i += RW_WARPS * 32) sm.chirp[i] = k1_ld_table4(p.down + 2 * i);
+    for (int i = threadIdx.x; i < RW_SPS; i += RW_WARPS * 32) { sm.up_ifreq[i] = __ldg(p.up_ifreq + i); sm.down_ifreq[i] = __ldg(p.down_ifreq + i); }
+    for (int i = threadIdx.x; i < 3 * RW_SPS; i += RW_WARPS * 32) sm.up_ifreq_v[i] = __ldg(p.up_ifreq_v + i);
+    __syncthreads();
+
+    const uint32_t local = blockIdx.x * RW_WARPS + warp;          // stream of this launch
+    if (local >= p.n_launch) return;                              // (no CTA barrier below)
+    const uint32_t stream = p.stream_base + local;
+    const float2 *xs = p.iq + (size_t)local * p.stride_items;
+    RWWarp &ws = sm.w[warp];
+    RxStreamState *gst = p.states + stream;
+    RxStreamState *st = &ws.st;
+    {   // decoder_impl members: global -> shared for the whole call
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(gst);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(st);
+        for (int i = lane; i < (int)(sizeof(RxStreamState) / 4); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
+    float2 *win = reinterpret_cast<float2 *>(ws.win);
+    float *ifq = ws.ifq;
+    lora_b200_step *trace = p.trace ? p.trace + (size_t)stream * p.trace_cap : nullptr;
+    W7Consts kc;
+    if (FFT) w7_consts(lane, p.tw, kc);
+
+    int state = st->state;
+    unsigned long long pos = 0;
+    unsigned int frames_here = 0, steps = 0;
+
+    while (true) {
+        if (pos + 2ull * (unsigned long long)sps > p.n_items) break;
+        if (frames_here >= p.max_frames_per_stream) break;
+        const float2 *x = xs + pos;
+        int consumed = 0, fine = 0, bin = -1, next_state = state;     // :749
+        float metric = 0.0f;
+
+        switch (state) {
+        case LORA_B200_DETECT: {                                  // :752-768, A8 :340-366
+            rw_load(x, win, 2 * sps, lane);
+            __syncwarp();
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+#pragma unroll 4
+            for (int i = lane; i < sps; i += 32) {
+                const float2 a = win[i], b = win[i + sps];
+                v0 += a.x * b.x + a.y * b.y;                      // a * conj(b)
+                v1 += a.y * b.x - a.x * b.y;
+                v2 += a.x * a.x + a.y * a.y;
+                v3 += b.x * b.x + b.y * b.y;
+            }
+            v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3 = warp_sum(v3);
+            const float s = sqrtf(v2 * v3);
+            const float corr = hypotf(v0 / s, v1 / s);            // :363
+            metric = corr;
+            if (lane == 0) {
+                st->energy_threshold = v3 / 2.0f;                 // :357
+                const float pw = v2 / (float)sps;                 // :360 push_back on the 4-deep ring
+                if (st->pwr_n < 4) { st->pwr_queue[(st->pwr_head + st->pwr_n) & 3] = pw; st->pwr_n++; }
+                else { st->pwr_queue[st->pwr_head] = pw; st->pwr_head = (st->pwr_head + 1) & 3; }
+                if (corr >= 0.90f) {                              // :755
+                    if (st->pwr_n >= 2)                           // determine_snr :377-383
+                        st->snr = st->pwr_queue[(st->pwr_head + st->pwr_n - 1) & 3] / st->pwr_queue[st->pwr_head];
+                    st->corr_fails = 0u;
+                }
+            }
+            if (corr >= 0.90f) next_state = LORA_B200_SYNC; else consumed = sps;
+            break;
+        }
+        case LORA_B200_SYNC: {                                    // :770-783, A9 :392-413
+            rw_load(x, win, 2 * sps, lane);
+            __syncwarp();
+            rw_ifreq(win, ifq, 2 * sps, lane);
+            // lag i = lane + 32 j, j = 0..31: products added in index order with separate multiply and add, like the
+            // reference's scalar dot product (cross_correlate_ifreq_fast -> volk_32f_x2_dot_prod_32f, :259-263)
+            float c[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) c[j] = 0.0f;
+            const float *f0 = ifq + lane;
+            for (int k = 0; k < sps - 1; k++) {
+                const float u = sm.up_ifreq[k];
+#pragma unroll
+                for (int j = 0; j < 32; j++) c[j] = __fadd_rn(c[j], __fmul_rn(f0[32 * j + k], u));
+            }
+            unsigned long long best = 0ull;
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const unsigned long long key = corr_key(c[j], (uint32_t)(lane + 32 * j));
+                best = key > best ? key : best;
+            }
+            best = warp_max_key(best);
+            metric = best ? key_mag2(best) : 0.0f;
+            consumed = best ? (int)key_idx(best) : 0;             // :780 consume_each(i)
+            next_state = LORA_B200_FIND_SFD;
+            if (p.cfo_estimate && lane == 0) {                    // experimental_determine_cfo(&input[i], sps), :730-738,774
+                const float2 m0 = cmul(win[consumed + 256], __ldg(p.down + 256)), m1 = cmul(win[consumed + 257], __ldg(p.down + 257));
+                const float p1 = atan2f(m0.y, m0.x);
+                float p2 = atan2f(m1.y, m1.x);
+                while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
+                while ((double)(p2 - p1) < -3.14159265358979323846) p2 = (float)((double)p2 + 6.283185307179586);
+                st->cfo_est = (float)((double)(p2 - p1) / (2.0 * 3.14159265358979323846) * (double)p.samples_per_second);
+                st->cfo_count++;
+            }
+            break;
+        }
+        case LORA_B200_FIND_SFD: {                                // :785-818, A10
+            rw_load(x, win, sps, lane);
+            __syncwarp();
+            rw_ifreq(win, ifq, sps, lane);
+            const int to_idx = sps - 1;
+            float s1 = 0.f;
+#pragma unroll 8
+            for (int i = lane; i < to_idx; i += 32) s1 += ifq[i];
+            s1 = warp_sum(s1);
+            const float average = s1 / (float)to_idx;             // :286
+            float q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+            for (int i = lane; i < to_idx; i += 32) {
+                const float t = ifq[i] - average;
+                q0 = fmaf(t, t, q0);                              // stddev :415-425
+                q1 = fmaf(t, sm.down_ifreq[i] - p.down_ifreq_avg, q1);
+            }
+            q0 = warp_sum(q0); q1 = warp_sum(q1);
+            const float sd = sqrtf(q0 / (float)to_idx) * p.down_ifreq_sd;   // :288-289
+            const float cc = q1 / sd / (float)to_idx;             // :291-295
+            const bool up_again = !(cc > 0.96f) && (cc < -0.97f);
+            if (up_again) fine = rw_fine_sync(ifq, sm.up_ifreq_v, -1, 32, lane);   // :803, decim * 4
+            metric = cc;
+            if (cc > 0.96f) {
+                next_state = LORA_B200_PAUSE;                     // :799
+            } else {
+                unsigned int fails = st->corr_fails;
+                if (!up_again) fails++;                           // :805
+                __syncwarp();
+                if (lane == 0) st->corr_fails = fails;
+                if (fails > 4u) next_state = LORA_B200_DETECT;    // :808-813
+            }
+            consumed = sps + fine;                                // :816
+            break;
+        }
+        case LORA_B200_PAUSE: {                                   // :820-824
+            next_state = LORA_B200_DECODE_HEADER;
+            consumed = sps + sps / 4;
+            break;
+        }
+        case LORA_B200_DECODE_HEADER:
+        case LORA_B200_DECODE_PAYLOAD: {                          // :826-886
+            const bool is_first = state == LORA_B200_DECODE_HEADER;
+            rw_load(x, win, sps, lane);
+            __syncwarp();
+            bool do_demod = true;
+            if (!is_first && p.implicit) {                        // :861 determine_energy
+                float e = 0.f;
+#pragma unroll 8
+                for (int i = lane; i < sps; i += 32) { const float2 a = win[i]; e += a.x * a.x + a.y * a.y; }
+                e = warp_sum(e);
+                if (e < st->energy_threshold) do_demod = false;
+            }
+            if (do_demod) {                                       // demodulate(), :493-529
+                if (!FFT || p.enable_fine_sync) rw_ifreq(win, ifq, sps, lane);
+                if (FFT) {                                        // get_shift_fft (:430-464) as in k1_sf7_warp_kernel, window in place
+                    float2 v0[16], v1[16];
+                    w7_pass0(lane, ws.win, sm.chirp, v0, v1);
+                    __syncwarp();
+                    w7_store(lane, ws.win, v0, v1);
+                    __syncwarp();
+                    float2 P[8], Pq;
+                    w7_pass1(lane, ws.win, kc, P, Pq);
+                    const int h = lane & 1;
+                    float2 own[4], other[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float2 send = h ? P[j] : P[4 + j];
+                        own[j] = h ? P[4 + j] : P[j];
+                        other[j].x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+                        other[j].y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+                    }
+                    float2 other_q;
+                    other_q.x = __shfl_xor_sync(0xffffffffu, Pq.x, 1);
+                    other_q.y = __shfl_xor_sync(0xffffffffu, Pq.y, 1);
+                    unsigned long long best = w7_final(lane, kc, own, other, Pq, other_q);
+                    best = warp_max_key(best);
+                    bin = ((int)key_idx(best) + N - 1) % N;       // gradient-index convention
+                } else {                                          // A5 :466-491
+                    float *avg = ifq + sps;
+#pragma unroll
+                    for (int m = 0; m < N / 32; m++) {
+                        const int i = lane + 32 * m;
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) acc += ifq[i * 8 + k];   // :475
+                        avg[i] = acc / 8.0f;                      // :476
+                    }
+                    __syncwarp();
+                    unsigned long long best = 0ull;
+#pragma unroll
+                    for (int m = 0; m < N / 32; m++) {
+                        const int i = lane + 32 * m;
+                        if (i >= 1) {
+                            const float g = avg[i - 1] - avg[i];  // :483
+                            if (g > 0.1f) { const unsigned long long k = pack_key(g, (uint32_t)i); best = k > best ? k : best; }
+                        }
+                    }
+                    best = warp_max_key(best);
+                    const int max_index = best ? (int)key_idx(best) + 1 : 0;   // :486
+                    bin = (N - max_index) % N;                    // :490
+                }
+                if (p.enable_fine_sync) fine = rw_fine_sync(ifq, sm.up_ifreq_v, bin, 2, lane);   // :501-502, max(decim / 4, 2)
+            }
+            int flag = 0;
+            unsigned int frame_slot = 0;
+            if (lane == 0) {
+                bool block_done = false;
+                uint32_t cr = st->phdr[1] >> 5;
+                if (do_demod) {
+                    const bool reduced = is_first || p.reduced_rate;      // :495
+                    uint32_t b = (uint32_t)bin;
+                    if (reduced) b = reduce_bin(b, p.n_bins_hdr);  // :507-509
+                    if (st->n_words < 8u) st->words[st->n_words] = gray_encode(b);    // :512,:517
+                    st->n_words++;
+                    if (st->n_words == 4u + (is_first ? 4u : cr)) {       // :521
+                        const uint32_t ppm = reduced ? p.sf - 2u : p.sf;
+                        uint8_t cwb[16];
+                        deinterleave_block(st->words, st->n_words, ppm, cwb);
+                        for (uint32_t k = 0; k < ppm; k++)
+                            if (st->n_demod < (uint32_t)LB_MAX_CW) st->demodulated[st->n_demod++] = cwb[k];
+                        st->n_words = 0;
+                        block_done = true;
+                    }
+                } else {
+                    st->payload_symbols = 0;                      // :862-864
+                    st->payload_length = st->n_demod / 2u;
+                }
+                if (is_first) {
+                    if (block_done) {
+                        if (p.implicit) {
+                            st->payload_symbols = 1;              // :829
+                        } else {
+                            const uint32_t nb = decode_len_bytes(6u, cr);            // decode(true) :831
+                            uint8_t hb[4] = {0, 0, 0, 0};
+                            for (uint32_t k = 0; k < nb && k < 4u; k++) hb[k] = decode_byte(st->demodulated, st->n_demod, 1, cr, k);
+                            st->n_hdr_print = (uint8_t)(nb < 4u ? nb : 4u);          // :832 prints d_decoded
+                            for (int k = 0; k < 4; k++) st->hdr_print[k] = hb[k];
+                            const uint32_t erase = st->n_demod < 5u ? st->n_demod : 5u;   // :632
+                            for (uint32_t k = erase; k < st->n_demod; k++) st->demodulated[k - erase] = st->demodulated[k];
+                            st->n_demod -= erase;
+                            st->phdr[0] = hb[0]; st->phdr[1] = hb[1]; st->phdr[2] = hb[2];   // :833
+                            if ((st->phdr[1] >> 5) > 4) st->phdr[1] = (uint8_t)((st->phdr[1] & 0x1f) | (4u << 5));   // :834-835
+                            cr = st->phdr[1] >> 5;
+                            st->payload_length = st->phdr[0] + 2u * ((st->phdr[1] >> 4) & 1u);   // :838
+                            st->payload_symbols = payload_symbols(st->payload_length, cr, p.sf, p.reduced_rate);
+                        }
+                        flag = 2;                                 // -> DECODE_PAYLOAD, :853
+                    }
+                } else {
+                    if (block_done && !p.implicit) st->payload_symbols -= (int32_t)(4u + cr);   // :866-867
+                    if (st->payload_symbols <= 0) {               // :870
+                        flag = 1;
+                        frame_slot = atomicAdd(p.n_frames, 1u);
+                    }
+                }
+            }
+            flag = __shfl_sync(0xffffffffu, flag, 0);
+            frame_slot = __shfl_sync(0xffffffffu, frame_slot, 0);
+            if (flag == 2) next_state = LORA_B200_DECODE_PAYLOAD;
+            consumed = sps + fine;                                // :856,:883
+            if (flag == 1) {                                      // decode(false) + msg_lora_frame happen in K8
+                if (frame_slot < p.frame_cap) {
+                    RxFrameRec *fr = p.frames + frame_slot;
+                    const uint32_t n = st->n_demod;
+                    for (uint32_t k = lane; k < n; k += 32) fr->cw[k] = st->demodulated[k];
+                    if (lane == 0) {
+                        fr->stream = stream; fr->seq = st->frame_seq++; fr->n_cw = n; fr->cr = st->phdr[1] >> 5;
+                        fr->payload_length = st->payload_length; fr->snr = st->snr;
+                        fr->phdr[0] = st->phdr[0]; fr->phdr[1] = st->phdr[1]; fr->phdr[2] = st->phdr[2];
+                        fr->n_hdr_print = p.implicit ? 0 : st->n_hdr_print;
+                        for (int k = 0; k < 4; k++) fr->hdr_print[k] = st->hdr_print[k];
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) { st->n_words = 0; st->n_demod = 0; }     // :875-880
+                next_state = LORA_B200_DETECT;
+                frames_here++;
+            }
+            break;
+        }
+        default: {                                                // STOP :888-891
+            consumed = sps;
+            break;
+        }
+        }
+        if (lane == 0 && trace && steps < p.trace_cap) {
+            lora_b200_step t;
+            t.state = state; t.consumed = consumed; t.bin = bin; t.fine_sync = fine; t.metric = metric;
+            trace[steps] = t;
+        }
+        steps++;
+        pos += (unsigned long long)(consumed > 0 ? consumed : 0);
+        state = next_state;
+        __syncwarp();                                             // the window and the state are rewritten by the next step
+    }
+    if (lane == 0) st->state = state;
+    __syncwarp();
+    {
+        uint32_t *dst = reinterpret_cast<uint32_t *>(gst);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(st);
+        for (int i = lane; i < (int)(sizeof(RxStreamState) / 4); i += 32) dst[i] = src[i];
+    }
+    if (lane == 0) {
+        p.consumed[stream] = pos;
+        if (p.trace_n) p.trace_n[stream] = steps;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace lb

@@ -128,7 +128,20 @@ class decoder:
         self._emit_stdout(stream)
         return int(consumed.value)
 
-    def work_batch(self, iq, n_items=None, stride_items=None, host=None, sc16_scale=None):
+    FRAME_DTYPE = np.dtype([("stream", "<u4"), ("seq", "<u4"), ("len", "<u4"), ("n_hdr_print", "u1"), ("hdr_print", "u1", (4,)),
+                            ("pad", "u1", (3,)), ("bytes", "u1", (564,))])
+
+    def frames_last(self) -> np.ndarray:
+        """Structured array (FRAME_DTYPE) of the frames the last work call published, in delivery order: the bulk
+        alternative to one Python callback per frame (lora_b200_frames_last)."""
+        ptr = C.c_void_p(0)
+        n = int(self._L.lora_b200_frames_last(self._h, C.byref(ptr)))
+        if n == 0:
+            return np.zeros(0, self.FRAME_DTYPE)
+        buf = C.string_at(ptr.value, n * self.FRAME_DTYPE.itemsize)
+        return np.frombuffer(buf, dtype=self.FRAME_DTYPE)
+
+    def work_batch(self, iq, n_items=None, stride_items=None, host=None, sc16_scale=None, callbacks=True):
         """All streams at once. ``iq``: host ndarray [n_streams, n_items] (complex64, or int16 [n_streams, n_items, 2]
         together with ``sc16_scale``) or a device tensor/pointer.  ``sc16_scale`` selects the int16 I/Q entry point:
         the device computes x * scale, PCIe moves 4 bytes per sample."""
@@ -141,20 +154,23 @@ class decoder:
             assert x.ndim == 2 and x.shape[0] == self.n_streams
             ptr, n_items, stride_items, host = x.ctypes.data, x.shape[1], x.shape[1], 1
         else:
-            ptr = _dev_ptr(iq)
+            ptr = _dev_ptr(iq)                                    # device tensor, or a raw host / device address with host=1 / 0
             host = 0 if host is None else int(host)
             if stride_items is None:
                 stride_items = n_items
-        consumed = (C.c_size_t * self.n_streams)()
+        consumed = np.zeros(self.n_streams, dtype=np.uint64)      # size_t[n_streams]
+        cptr = consumed.ctypes.data_as(C.POINTER(C.c_size_t))
+        cb = self._cb if callbacks else N.FRAME_CB()              # callbacks=False: drain with frames_last() instead
         if sc16_scale is not None:
             N.check(self._L.lora_b200_work_batch_sc16(self._h, ptr, float(sc16_scale), int(n_items), int(stride_items), host,
-                                                      consumed, self._cb, None), "lora_b200_work_batch_sc16")
+                                                      cptr, cb, None), "lora_b200_work_batch_sc16")
         else:
-            N.check(self._L.lora_b200_work_batch(self._h, ptr, int(n_items), int(stride_items), host, consumed, self._cb, None),
+            N.check(self._L.lora_b200_work_batch(self._h, ptr, int(n_items), int(stride_items), host, cptr, cb, None),
                     "lora_b200_work_batch")
-        for s in range(self.n_streams):
-            self._emit_stdout(s)
-        return np.array(list(consumed), dtype=np.int64)
+        if not self.quiet:
+            for s in range(self.n_streams):
+                self._emit_stdout(s)
+        return consumed.astype(np.int64)
 
     def _emit_stdout(self, stream):
         if self.quiet:

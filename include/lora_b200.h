@@ -158,6 +158,19 @@ int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, s
  * lora_b200_work_batch on the host-converted buffer. */
 int lora_b200_work_batch_sc16(lora_b200_decoder *d, const void *iq_sc16, float scale, size_t n_items, size_t stride_items,
                               int host_ptr, size_t *consumed /* [n_streams] */, lora_b200_frame_cb cb, void *user);
+/* Bulk access to what the last work / work_batch call published, for hosts that drain thousands of streams per call and do
+ * not want one callback per frame (cb may be NULL then): records in delivery order (by stream, then by sequence), valid
+ * until the next work call on this decoder.  `bytes` = loratap | loraphy | payload, `len` of them valid
+ * (decoder_impl.cc:588-601); hdr_print = the header bytes the reference prints first (:832). */
+#define LORA_B200_MAX_FRAME_BYTES 564
+typedef struct lora_b200_frame {
+    uint32_t stream, seq, len;
+    uint8_t  n_hdr_print;
+    uint8_t  hdr_print[4];
+    uint8_t  pad[3];
+    uint8_t  bytes[LORA_B200_MAX_FRAME_BYTES];
+} lora_b200_frame;
+size_t lora_b200_frames_last(lora_b200_decoder *d, const lora_b200_frame **frames);
 /* current state of a stream (LORA_B200_DETECT ...) */
 int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream);
 /* N4: the CFO estimate the reference computes in experimental_determine_cfo (lib/decoder_impl.cc:730-738:

@@ -126,3 +126,23 @@ def test_demod_fft_host_sc16(torch, oracle, sf, n):
     np.testing.assert_allclose(m16, om, rtol=1e-4)
     assert np.mean(b16 == vals) > 0.999
     dec.close()
+
+
+def test_frames_last_equals_callbacks(torch, oracle):
+    """lora_b200_frames_last: the bulk view of what the last call published = the callback sequence (stream, bytes),
+    also when no callback is registered at all."""
+    import gr_lora_b200 as G
+    x, pays = _streams(7, 12, 2100)
+    n = x.shape[1]
+    dec = G.decoder(1e6, 125000, 7, False, 4, True, n_streams=12, quiet=True, max_items_per_call=n, max_frames_per_call=4)
+    dec.work_batch(x)
+    fr = dec.frames_last()
+    assert len(fr) == len(dec.frames) > 0
+    for rec, (s, f) in zip(fr, dec.frames):
+        assert int(rec["stream"]) == s and bytes(rec["bytes"][: int(rec["len"])]) == f
+    dec.close()
+    dec = G.decoder(1e6, 125000, 7, False, 4, True, n_streams=12, quiet=True, max_items_per_call=n, max_frames_per_call=4)
+    dec.work_batch(x, callbacks=False)
+    fr2 = dec.frames_last()
+    assert dec.frames == [] and fr2.tobytes() == fr.tobytes()
+    dec.close()
