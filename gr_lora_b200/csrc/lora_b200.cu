@@ -87,7 +87,8 @@ struct lora_b200_decoder {
     float *d_chunk_mags[2] = {nullptr, nullptr};
     size_t chunk_symbols = 0;
     // stream path
-    cudaStream_t rx_stream = nullptr;
+    cudaStream_t rx_stream = nullptr, rx_stream2 = nullptr;
+    cudaEvent_t rx2_done = nullptr, rx_begin_ev = nullptr;
     RxStreamState *d_states = nullptr;
     float *d_scratch = nullptr;
     unsigned long long *d_consumed = nullptr;
@@ -395,7 +396,8 @@ int rx_begin(lora_b200_decoder *d) {
 }
 
 // the state machine for streams [stream_base, stream_base + n_launch) over staged IQ (one CTA per stream), async on rx_stream
-int rx_launch(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t n_items, uint32_t stream_base, uint32_t n_launch) {
+int rx_launch(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t n_items, uint32_t stream_base, uint32_t n_launch,
+              cudaStream_t st = nullptr) {
     RxParams p;
     memset(&p, 0, sizeof p);
     p.iq = d_iq; p.stride_items = stride_items; p.n_items = n_items; p.stream_base = stream_base; p.n_launch = n_launch;
@@ -412,7 +414,7 @@ int rx_launch(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, siz
     p.frames = d->d_frames; p.n_frames = d->d_n_frames; p.frame_cap = d->frame_cap;
     p.max_frames_per_stream = d->cfg.max_frames_per_call;
     p.trace = d->d_trace; p.trace_cap = d->cfg.trace_capacity; p.trace_n = d->d_trace_n;
-    return launch_rx(d, p, (int)n_launch, d->rx_stream);
+    return launch_rx(d, p, (int)n_launch, st ? st : d->rx_stream);
 }
 
 // K8 on the queued frames, results back to the host, frames delivered per stream in sequence order
@@ -602,6 +604,9 @@ void lora_b200_destroy(lora_b200_decoder *d) {
         if (d->h_chunk[i]) cudaFreeHost(d->h_chunk[i]);
     }
     if (d->rx_stream) cudaStreamDestroy(d->rx_stream);
+    if (d->rx_stream2) cudaStreamDestroy(d->rx_stream2);
+    if (d->rx2_done) cudaEventDestroy(d->rx2_done);
+    if (d->rx_begin_ev) cudaEventDestroy(d->rx_begin_ev);
     cudaFree(d->d_states); cudaFree(d->d_scratch); cudaFree(d->d_consumed); cudaFree(d->d_frames);
     cudaFree(d->d_frames_out); cudaFree(d->d_n_frames); cudaFree(d->d_trace); cudaFree(d->d_trace_n);
     cudaFree(d->d_stage); cudaFree(d->d_stage16);
@@ -834,9 +839,18 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
     int rc = ensure_stage(d, n_items * ns, false, sc16);
     if (rc) return rc;
     if (!d->copy_streams[0]) CU(cudaStreamCreateWithFlags(&d->copy_streams[0], cudaStreamNonBlocking));
-    // groups: as many as keep every launch at least two CTAs per SM wide (a group is one launch; small batches stay whole)
-    const uint32_t n_groups = std::max<uint32_t>(1u, std::min<uint32_t>(8u, ns / (2u * (uint32_t)d->n_sms)));
+    // groups: one launch each; a group should fill the machine at least once (rx_warp_kernel: 9 streams per CTA, one CTA per
+    // SM; rx_stream_kernel: one stream per CTA, two CTAs per SM), small batches stay whole.  Consecutive groups run on two
+    // alternating compute streams so that the tail of one launch overlaps the head of the next.
+    const bool warp_kernel = d->cfg.sf == 7 && d->sps == (uint32_t)RW_SPS;
+    const uint32_t per_wave = (uint32_t)d->n_sms * (warp_kernel ? (uint32_t)RW_WARPS : 2u);
+    const uint32_t n_groups = std::max<uint32_t>(1u, std::min<uint32_t>(8u, ns / per_wave));
     const uint32_t gs = (ns + n_groups - 1) / n_groups;
+    if (!d->rx_stream2) {
+        CU(cudaStreamCreateWithFlags(&d->rx_stream2, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&d->rx2_done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&d->rx_begin_ev, cudaEventDisableTiming));
+    }
     if (d->stage_events.size() < n_groups) {
         const size_t have = d->stage_events.size();
         d->stage_events.resize(n_groups, nullptr);
@@ -844,23 +858,28 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
     }
     cudaStream_t cs = d->copy_streams[0];
     if ((rc = rx_begin(d))) return rc;
+    CU(cudaEventRecord(d->rx_begin_ev, d->rx_stream));            // the frame counter is reset before any group runs
+    CU(cudaStreamWaitEvent(d->rx_stream2, d->rx_begin_ev, 0));
     for (uint32_t g = 0; g * gs < ns; g++) {
         const uint32_t s0 = g * gs, cnt = std::min<uint32_t>(gs, ns - s0);
+        cudaStream_t xs = (g & 1) ? d->rx_stream2 : d->rx_stream;
         const uint8_t *src = (const uint8_t *)iq + (size_t)s0 * stride_items * elem;
         void *dst = sc16 ? (void *)(d->d_stage16 + (size_t)s0 * n_items) : (void *)(d->d_stage + (size_t)s0 * n_items);
         CU(cudaMemcpy2DAsync(dst, elem * n_items, src, elem * stride_items, elem * n_items, cnt,
                              host_ptr ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
         CU(cudaEventRecord(d->stage_events[g], cs));
-        CU(cudaStreamWaitEvent(d->rx_stream, d->stage_events[g], 0));
+        CU(cudaStreamWaitEvent(xs, d->stage_events[g], 0));
         if (sc16) {
             const size_t n = (size_t)cnt * n_items;
             const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)d->n_sms * 8);
-            sc16_to_cf32_kernel<<<grid, 256, 0, d->rx_stream>>>(d->d_stage16 + (size_t)s0 * n_items, d->d_stage + (size_t)s0 * n_items, n, scale);
+            sc16_to_cf32_kernel<<<grid, 256, 0, xs>>>(d->d_stage16 + (size_t)s0 * n_items, d->d_stage + (size_t)s0 * n_items, n, scale);
             d->launches++;
             CU(cudaGetLastError());
         }
-        if ((rc = rx_launch(d, d->d_stage + (size_t)s0 * n_items, n_items, n_items, s0, cnt))) return rc;
+        if ((rc = rx_launch(d, d->d_stage + (size_t)s0 * n_items, n_items, n_items, s0, cnt, xs))) return rc;
     }
+    CU(cudaEventRecord(d->rx2_done, d->rx_stream2));
+    CU(cudaStreamWaitEvent(d->rx_stream, d->rx2_done, 0));
     return rx_finish(d, 0, ns, consumed, cb, user);
 }
 

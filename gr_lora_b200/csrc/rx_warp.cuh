@@ -22,11 +22,11 @@
 
 namespace lb {
 
-constexpr int RW_SPS = 1024, RW_N = 128, RW_WARPS = 7;
+constexpr int RW_SPS = 1024, RW_N = 128, RW_WARPS = 9;       // 9 warps x ~213 registers fill the register file; 184 KiB of shared memory
 
 #ifdef __CUDACC__
 struct RWWarp {
-    float4 win[RW_SPS];               // 2 * sps samples (float2) of the current step
+    float4 win[RW_SPS / 2];           // sps samples (float2): the window of the SFD / decode steps (DETECT and SYNC stream from global)
     float ifq[2 * RW_SPS];            // instantaneous frequency of the window; [sps, sps + N) doubles as the bin averages
     RxStreamState st;
 };
@@ -44,7 +44,7 @@ LB_D void rw_load(const float2 *__restrict__ g, float2 *win, int n, int lane) {
     for (int k = lane; k < n; k += 32) win[k] = __ldcs(g + k);
 }
 
-// A3 instantaneous_frequency (:224-244) of win[0, w) into out[0, w); one atan2f per sample
+// A3 instantaneous_frequency (:224-244) of win[0, w) (shared or global memory) into out[0, w); one atan2f per sample
 LB_D void rw_ifreq(const float2 *win, float *out, int w, int lane) {
     float a_cur;
     { const float2 s = win[lane]; a_cur = atan2f(s.y, s.x); }
@@ -137,12 +137,10 @@ rx_warp_kernel(RxParams p) {
 
         switch (state) {
         case LORA_B200_DETECT: {                                  // :752-768, A8 :340-366
-            rw_load(x, win, 2 * sps, lane);
-            __syncwarp();
             float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
-#pragma unroll 4
+#pragma unroll 8
             for (int i = lane; i < sps; i += 32) {
-                const float2 a = win[i], b = win[i + sps];
+                const float2 a = __ldcs(x + i), b = __ldcs(x + i + sps);
                 v0 += a.x * b.x + a.y * b.y;                      // a * conj(b)
                 v1 += a.y * b.x - a.x * b.y;
                 v2 += a.x * a.x + a.y * a.y;
@@ -167,9 +165,7 @@ rx_warp_kernel(RxParams p) {
             break;
         }
         case LORA_B200_SYNC: {                                    // :770-783, A9 :392-413
-            rw_load(x, win, 2 * sps, lane);
-            __syncwarp();
-            rw_ifreq(win, ifq, 2 * sps, lane);
+            rw_ifreq(x, ifq, 2 * sps, lane);                     // straight from global memory: every sample is touched once
             // lag i = lane + 32 j, j = 0..31: products added in index order with separate multiply and add, like the
             // reference's scalar dot product (cross_correlate_ifreq_fast -> volk_32f_x2_dot_prod_32f, :259-263)
             float c[32];
@@ -192,7 +188,7 @@ rx_warp_kernel(RxParams p) {
             consumed = best ? (int)key_idx(best) : 0;             // :780 consume_each(i)
             next_state = LORA_B200_FIND_SFD;
             if (p.cfo_estimate && lane == 0) {                    // experimental_determine_cfo(&input[i], sps), :730-738,774
-                const float2 m0 = cmul(win[consumed + 256], __ldg(p.down + 256)), m1 = cmul(win[consumed + 257], __ldg(p.down + 257));
+                const float2 m0 = cmul(x[consumed + 256], __ldg(p.down + 256)), m1 = cmul(x[consumed + 257], __ldg(p.down + 257));
                 const float p1 = atan2f(m0.y, m0.x);
                 float p2 = atan2f(m1.y, m1.x);
                 while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
