@@ -68,7 +68,8 @@ template <int SF> struct RLate { static constexpr int EARLY = RCfg<SF>::NSLOT - 
 //   chirp   [64 (warp >> 2), +64)        c[j][b] of the thread's pass-0 samples, word 4 j + 2 b + {re, im}
 //   tw0     [256 + 32 (warp >> 2), +32)  W_L^{a kc}, kc = 1..15, word 2 (kc - 1) + {re, im}
 //   tw1     [384, +32)                   W_{L/16}^{a0 kb}, kb = 1..15 (a function of the lane only: shared by 4 warps)
-constexpr int R_TM_COLS = 512, R_TM_CHIRP = 0, R_TM_TW0 = 256, R_TM_TW1 = 384;
+//   stash   [416 + 16 (warp >> 2), +16)  SF12: the lane's 8 partial sums of the previous symbol until the peer's have arrived
+constexpr int R_TM_COLS = 512, R_TM_CHIRP = 0, R_TM_TW0 = 256, R_TM_TW1 = 384, R_TM_STASH = 416;
 
 // ---- index arithmetic --------------------------------------------------------------------------------------------------
 template <int SF> LB_HD int r_a0(int lane) { return lane / RCfg<SF>::CPA; }
@@ -204,10 +205,10 @@ LB_D void mbar_arrive_peer(uint32_t peer_bar_addr) {
 LB_D void mbar_arrive_peer_relaxed(uint32_t peer_bar_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar_addr) : "memory");
 }
-// shared::cta -> the peer CTA's shared memory through the async proxy; the bytes are counted on the PEER's mbarrier
-LB_D void bulk_s2peer(uint32_t peer_dst, uint32_t local_src, uint32_t bytes, uint32_t peer_bar) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(peer_dst), "r"(local_src), "r"(bytes), "r"(peer_bar) : "memory");
+// 16 bytes from registers into the peer CTA's shared memory through the async proxy; counted on the PEER's mbarrier
+LB_D void st_async_peer_f4(uint32_t peer_dst, float4 v, uint32_t peer_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+                 ::"r"(peer_dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(peer_bar) : "memory");
 }
 LB_D void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // acquire at cluster scope: the peer's DSMEM stores are visible after it
     uint32_t ok;
@@ -230,14 +231,14 @@ LB_D void tma_rows_2d(void *dst_smem, const void *tmap, int c0, int c1, uint64_t
 template <int SF>
 struct RSmem {
     float4 slots[RCfg<SF>::NSLOT][RCfg<SF>::ROW_F4];
-    // SF12 only: partial sums of the bins the PEER finishes, per warp pair a block of [kb][h][8] complex + the bin-N/2 extra
-    // (258 complex = 2064 bytes): staged in `send`, moved by cp.async.bulk into the peer's `recv`
-    float2 recv[RCfg<SF>::CL == 2 ? 8 * 258 : 2];
-    float2 send[RCfg<SF>::CL == 2 ? 8 * 258 : 2];
+    // SF12 only: the peer's partial sums of the bins THIS CTA finishes, written by the peer's st.async.  Two buffers (symbol
+    // parity) of one 2 KiB block per warp pair, a block = 128 float4 = [i][lane] (i = 0..3: the lane's bins 2i, 2i+1), lane-major
+    // inside each i so that the 128-bit reads of a quarter warp fall into 8 different bank groups
+    float2 recv[RCfg<SF>::CL == 2 ? 2 * 8 * 256 : 2];
     unsigned long long keys[2][RCfg<SF>::NW];
     uint64_t sym_full[R_NSYM_BAR];                        // early rows of a symbol
     uint64_t sym_late[R_NSYM_BAR];                        // its last 16 - EARLY rows
-    uint64_t x_full[8], x_free[8];                        // SF12: per receiving / sending warp pair
+    uint64_t x_full[16], x_free[16];                      // SF12: per buffer and receiving / sending warp pair, index 8 b + i
     uint32_t tm_base;
 };
 
@@ -268,10 +269,11 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
 #pragma unroll
         for (int i = 0; i < R_NSYM_BAR; i++) { mbar_init(&sm.sym_full[i], RLate<SF>::EARLY); mbar_init(&sm.sym_late[i], 16 - RLate<SF>::EARLY); }
 #pragma unroll
-        for (int i = 0; i < 8; i++) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_free[i], 32); }     // full: one expect_tx + the copy's bytes; free: every lane
+        for (int i = 0; i < 16; i++) { mbar_init(&sm.x_full[i], 1); mbar_init(&sm.x_free[i], 32); }     // full: one expect_tx + the stores' bytes; free: every lane
         if (C::CL == 2 && n_mine > 0)
 #pragma unroll
-            for (int i = 0; i < 8; i++) mbar_expect_tx(&sm.x_full[i], 258u * 8u);     // phase 0 of the receive barriers
+            for (int i = 0; i < 16; i++)
+                if (i < 8 || n_mine > 1) mbar_expect_tx(&sm.x_full[i], 2048u);          // phase 0 of the receive barriers (symbols 0 and 1)
         fence_mbar_init();
     }
     if (warp == 0) tm_alloc(&sm.tm_base);
@@ -353,6 +355,46 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
     // pass 2: unit = K ^ m with K = (a0, e) a compile-time number and m = (the lane pair's bit) ^ swizzle(kb) a lane constant;
     // only the low three unit bits meet m, so 4 XORed addresses per symbol cover all 16 loads
     const uint32_t m2 = (uint32_t)((SF == 11 ? 2 * (lane & 1) : (lane & 1)) ^ r_swz<SF>(lane >> 1)) * 16u + (uint32_t)(lane >> 1) * 512u;
+    // SF12 exchange roles: warp pair x_i; this CTA finishes the bins of rows kc with (kc >> 3) == rank
+    const int x_i = warp & 7;
+    const bool x_mine = C::CL == 2 && (uint32_t)(warp >> 3) == rank;
+    auto finalize_prev = [&](size_t sp) {          // receiver warps: own sums (tensor memory) + the peer's (recv) of symbol sp -> argmax
+        const int xb = (int)(sp & 1) * 8 + x_i;
+        mbar_wait(&sm.x_full[xb], (uint32_t)((sp >> 1) & 1));
+        float2 o[8];
+        tm_ld16(tm_lane + (uint32_t)(R_TM_STASH + 16 * (warp >> 2)), o);
+        const float4 *rblk = reinterpret_cast<const float4 *>(&sm.recv[xb * 256]);
+        float4 u[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) u[i] = rblk[i * 32 + lane];
+        tm_wait_ld();
+        uint32_t dep = 0;
+        unsigned long long bk = 0ull;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 fa = cadd(o[2 * i], make_float2(u[i].x, u[i].y));
+            const float2 fb = cadd(o[2 * i + 1], make_float2(u[i].z, u[i].w));
+            dep |= __float_as_uint(u[i].w);
+            const int q0 = 2 * i + (lane & 1) * (C::A0 / 2);
+            const unsigned long long ka = pack_key(cnorm2(fa), (uint32_t)(warp + 16 * (lane >> 1) + 256 * q0));
+            const unsigned long long kb = pack_key(cnorm2(fb), (uint32_t)(warp + 16 * (lane >> 1) + 256 * (q0 + 1)));
+            bk = ka > bk ? ka : bk;
+            bk = kb > bk ? kb : bk;
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, off);
+            bk = ok > bk ? ok : bk;
+        }
+        if (lane == 0) {
+            atomicMax(P.packed + unit + sp * n_units, bk);
+            if (sp + 2 < n_mine) mbar_expect_tx(&sm.x_full[xb], 2048u);     // arm the buffer's next phase (this one has completed)
+        }
+        // tell the peer the block has been read: the arrive carries no data (relaxed), but it must not be issued before this
+        // lane's loads have returned, so its address depends on them
+        asm volatile("and.b32 %0, %0, 0;" : "+r"(dep));
+        mbar_arrive_peer_relaxed(map_to_peer(smem_u32(&sm.x_free[xb]), peer) + dep);
+    };
     int base = 0;
     for (size_t s = 0; s < n_mine; s++, base = base + 16 >= C::NSLOT ? base + 16 - C::NSLOT : base + 16) {
         const size_t g0 = s * 16;
@@ -398,7 +440,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         }
         __syncthreads();
         // result of the previous symbol (its keys were complete before this barrier)
-        if (s > 0 && warp == 0) {
+        if (C::CL == 1 && s > 0 && warp == 0) {
             unsigned long long k = lane < C::NW ? sm.keys[(s - 1) & 1][lane] : 0ull;
 #pragma unroll
             for (int off = 8; off > 0; off >>= 1) {
@@ -436,6 +478,9 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         }
         __syncwarp();
         // ---- pass 2: radix A0 over a0, branch sum, argmax ---------------------------------------------------------------
+        // SF12: the sums of the PREVIOUS symbol are completed first -- the peer's half has had a whole symbol time to arrive,
+        // so the wait below does not stall (second capture: 9 % of all samples waited for the peer's block of the same symbol)
+        if (C::CL == 2 && x_mine && s > 0) finalize_prev(s - 1);
         unsigned long long best = 0ull;
         {
             float2 g[C::HB][C::A0];
@@ -503,52 +548,22 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 tq = cadd(tq, got);
             }
             if (C::CL == 2) {
-                // bins of rows kc < 8 are finished by CTA 0, kc >= 8 by CTA 1: the other CTA sends its partial sums.  The
-                // block travels through the async proxy (cp.async.bulk shared::cta -> shared::cluster, complete_tx on the
-                // peer's mbarrier), so the receiver needs no cluster-scope acquire and the sender no cluster-scope fence: in
-                // the first version those compiled to MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL and held 30 % of all stall samples.
-                const int xi = warp & 7;
-                const bool mine = (uint32_t)(warp >> 3) == rank;
-                // block of warp pair xi: 129 float4 = [i][lane] (i = 0..3: the lane's bins 2i, 2i+1) + the bin-N/2 extra at float4 128;
-                // lane-major inside each i, so the 128-bit accesses of a quarter warp fall into 8 different bank groups
-                float4 *sblk = reinterpret_cast<float4 *>(&sm.send[xi * 258]);
-                const float4 *rblk = reinterpret_cast<const float4 *>(&sm.recv[xi * 258]);
-                if (!mine) {
-                    if (s > 0) mbar_wait(&sm.x_free[xi], (uint32_t)((s - 1) & 1));     // the peer has consumed the previous block (so the copy has read `send`)
+                // bins of rows kc < 8 are finished by CTA 0, kc >= 8 by CTA 1.  The other CTA sends its partial sums straight
+                // from registers through the async proxy (st.async ... mbarrier::complete_tx on the peer's barrier): no staging,
+                // no cluster-scope fence or acquire (the first version's DSMEM stores + fence.acq_rel.cluster +
+                // try_wait.acquire.cluster compiled to MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL: 30 % of all stall samples).
+                if (quirk_warp && lane == 1) f[0] = cadd(f[0], tq);      // both evaluations of bin N/2 are additive
+                if (!x_mine) {
+                    const int xb = (int)(s & 1) * 8 + x_i;
+                    if (s > 1) mbar_wait(&sm.x_free[xb], (uint32_t)(((s >> 1) - 1) & 1));     // the peer has consumed symbol s - 2 (a symbol time ago)
+                    const uint32_t dst = map_to_peer(smem_u32(&sm.recv[xb * 256]), peer) + (uint32_t)lane * 16u;
+                    const uint32_t bar = map_to_peer(smem_u32(&sm.x_full[xb]), peer);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) sblk[i * 32 + lane] = make_float4(f[2 * i].x, f[2 * i].y, f[2 * i + 1].x, f[2 * i + 1].y);
-                    if (quirk_warp && lane == 1) sm.send[xi * 258 + 256] = tq;
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0)
-                        bulk_s2peer(map_to_peer(smem_u32(&sm.recv[xi * 258]), peer), smem_u32(&sm.send[xi * 258]), 258u * 8u,
-                                    map_to_peer(smem_u32(&sm.x_full[xi]), peer));
+                    for (int i = 0; i < 4; i++) st_async_peer_f4(dst + (uint32_t)i * 512u, make_float4(f[2 * i].x, f[2 * i].y, f[2 * i + 1].x, f[2 * i + 1].y), bar);
                 } else {
-                    mbar_wait(&sm.x_full[xi], (uint32_t)(s & 1));
-                    uint32_t dep = 0;
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float4 u = rblk[i * 32 + lane];
-                        f[2 * i] = cadd(f[2 * i], make_float2(u.x, u.y));
-                        f[2 * i + 1] = cadd(f[2 * i + 1], make_float2(u.z, u.w));
-                        dep |= __float_as_uint(u.w);
-                    }
-                    if (quirk_warp && lane == 1) tq = cadd(tq, sm.recv[xi * 258 + 256]);
-                    if (quirk_warp && lane == 1) dep |= __float_as_uint(tq.x);
-                    if (lane == 0 && s + 1 < n_mine) mbar_expect_tx(&sm.x_full[xi], 258u * 8u);      // arm the next phase (this one has completed)
-                    // tell the peer the block has been read: the arrive carries no data (relaxed), but it must not be
-                    // issued before this lane's loads have returned, so its address depends on them
-                    asm volatile("and.b32 %0, %0, 0;" : "+r"(dep));
-                    mbar_arrive_peer_relaxed(map_to_peer(smem_u32(&sm.x_free[xi]), peer) + dep);
-                }
-                if (mine) {
-                    if (quirk_warp && lane == 1) f[0] = cadd(f[0], tq);
-#pragma unroll
-                    for (int i = 0; i < C::A0 / 2; i++) {
-                        const int q2 = i + h2 * (C::A0 / 2);
-                        const unsigned long long key = pack_key(cnorm2(f[i]), (uint32_t)(warp + 16 * kb2 + 256 * q2));
-                        best = key > best ? key : best;
-                    }
+                    // own half: parked in tensor memory until the next pass 2 (finalize_prev)
+                    tm_st16(tm_lane + (uint32_t)(R_TM_STASH + 16 * (warp >> 2)), f);
+                    tm_wait_st();
                 }
             } else {
                 if (quirk_warp && lane == 1) f[0] = cadd(f[0], tq);
@@ -565,10 +580,11 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
             const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
             best = o > best ? o : best;
         }
-        if (lane == 0) sm.keys[s & 1][warp] = best;
+        if (C::CL == 1 && lane == 0) sm.keys[s & 1][warp] = best;
     }
+    if (C::CL == 2 && x_mine && n_mine > 0) finalize_prev(n_mine - 1);
     __syncthreads();
-    if (n_mine > 0 && warp == 0) {
+    if (C::CL == 1 && n_mine > 0 && warp == 0) {
         unsigned long long k = lane < C::NW ? sm.keys[(n_mine - 1) & 1][lane] : 0ull;
 #pragma unroll
         for (int off = 8; off > 0; off >>= 1) {

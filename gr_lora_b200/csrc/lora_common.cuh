@@ -14,6 +14,12 @@
 
 namespace lb {
 
+// The largest float below the double M_PI (0x40490FDA; the next float, 0x40490FDB, is above it).  The reference unwraps phase
+// differences with "while ((phase2 - phase) > M_PI)" (lib/decoder_impl.cc:236-237): a float difference promoted to double.
+// For a float d, (double)d > M_PI  <=>  d > LB_PI_BELOW, and (double)d < -M_PI  <=>  d < -LB_PI_BELOW, exactly -- the test
+// needs no fp64 conversion / compare per sample (they were 15 % of the stream kernel's stall samples, profiles/r2_rx_sf7_warp.txt).
+#define LB_PI_BELOW 3.14159250259399414f
+
 // ---- complex arithmetic ---------------------------------------------------------------------
 // On the device every complex value lives in an aligned 64-bit register pair and the arithmetic uses
 // Blackwell's packed fp32 instructions (PTX add/sub/mul/fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2,

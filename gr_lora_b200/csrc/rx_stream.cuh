@@ -182,8 +182,8 @@ LB_D void ifreq_block(const float2 *__restrict__ x, float *__restrict__ out, int
         if (lane == 0 && active) { const float2 s = x[i - 1]; p1 = atan2f(s.y, s.x); }
         if (active) {
             // :236-237, float difference against the double M_PI, correction in double
-            while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
-            while ((double)(p2 - p1) < -3.14159265358979323846) p2 = (float)((double)p2 + 6.283185307179586);
+            while (p2 - p1 > LB_PI_BELOW) p2 = (float)((double)p2 - 6.283185307179586);
+            while (p2 - p1 < -LB_PI_BELOW) p2 = (float)((double)p2 + 6.283185307179586);
             out[i - 1] = p2 - p1;
         }
     }
@@ -302,8 +302,8 @@ rx_stream_kernel(RxParams p) {
                     const float2 m0 = cmul(xi[256], __ldg(p.down + 256)), m1 = cmul(xi[257], __ldg(p.down + 257));
                     const float p1 = atan2f(m0.y, m0.x);
                     float p2 = atan2f(m1.y, m1.x);
-                    while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
-                    while ((double)(p2 - p1) < -3.14159265358979323846) p2 = (float)((double)p2 + 6.283185307179586);
+                    while (p2 - p1 > LB_PI_BELOW) p2 = (float)((double)p2 - 6.283185307179586);
+                    while (p2 - p1 < -LB_PI_BELOW) p2 = (float)((double)p2 + 6.283185307179586);
                     st->cfo_est = (float)((double)(p2 - p1) / (2.0 * 3.14159265358979323846) * (double)p.samples_per_second);
                     st->cfo_count++;
                 }

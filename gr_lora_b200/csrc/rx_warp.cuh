@@ -59,8 +59,8 @@ LB_D void rw_ifreq(const float2 *win, float *out, int w, int lane) {
             const float p1 = a_cur;
             float p2 = lane == 31 ? n2 : n1;
             // :236-237, float difference against the double M_PI, correction in double
-            while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
-            while ((double)(p2 - p1) < -3.14159265358979323846) p2 = (float)((double)p2 + 6.283185307179586);
+            while (p2 - p1 > LB_PI_BELOW) p2 = (float)((double)p2 - 6.283185307179586);
+            while (p2 - p1 < -LB_PI_BELOW) p2 = (float)((double)p2 + 6.283185307179586);
             out[j] = p2 - p1;
         }
         a_cur = a_nxt;
@@ -191,8 +191,8 @@ rx_warp_kernel(RxParams p) {
                 const float2 m0 = cmul(x[consumed + 256], __ldg(p.down + 256)), m1 = cmul(x[consumed + 257], __ldg(p.down + 257));
                 const float p1 = atan2f(m0.y, m0.x);
                 float p2 = atan2f(m1.y, m1.x);
-                while ((double)(p2 - p1) > 3.14159265358979323846) p2 = (float)((double)p2 - 6.283185307179586);
-                while ((double)(p2 - p1) < -3.14159265358979323846) p2 = (float)((double)p2 + 6.283185307179586);
+                while (p2 - p1 > LB_PI_BELOW) p2 = (float)((double)p2 - 6.283185307179586);
+                while (p2 - p1 < -LB_PI_BELOW) p2 = (float)((double)p2 + 6.283185307179586);
                 st->cfo_est = (float)((double)(p2 - p1) / (2.0 * 3.14159265358979323846) * (double)p.samples_per_second);
                 st->cfo_count++;
             }
