@@ -261,11 +261,7 @@ k1_fft_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags,
         }
         unsigned long long best = k1_combine<SF>(a, s, tid, buf, wtab);
         // warp argmax, then across the warps of one symbol
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o > best ? o : best;
-        }
+        best = warp_max_key(best);
         if ((tid & 31) == 0) warp_best[tid >> 5] = best;
         __syncthreads();
         if (tid < C::G) {

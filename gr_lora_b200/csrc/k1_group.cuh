@@ -353,11 +353,7 @@ k1_group_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags)
             group_bar(bar_id, C::T);
             best = g_combine_p<SF>(t, reinterpret_cast<const float2 *>(slot), sm.quirk[grp], c);
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o > best ? o : best;
-        }
+        best = warp_max_key(best);
         if (lane == 0) sm.keys[grp][wig] = best;
         group_bar(bar_id, C::T);                        // exchange-2 reads done + keys visible
         if (t == 0) {

@@ -381,11 +381,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
             bk = ka > bk ? ka : bk;
             bk = kb > bk ? kb : bk;
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, bk, off);
-            bk = ok > bk ? ok : bk;
-        }
+        bk = warp_max_key(bk);
         if (lane == 0) {
             atomicMax(P.packed + unit + sp * n_units, bk);
             if (sp + 2 < n_mine) mbar_expect_tx(&sm.x_full[xb], 2048u);     // arm the buffer's next phase (this one has completed)
@@ -442,11 +438,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         // result of the previous symbol (its keys were complete before this barrier)
         if (C::CL == 1 && s > 0 && warp == 0) {
             unsigned long long k = lane < C::NW ? sm.keys[(s - 1) & 1][lane] : 0ull;
-#pragma unroll
-            for (int off = 8; off > 0; off >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
-                k = o > k ? o : k;
-            }
+            k = warp_max_key(k);      // lanes >= NW hold 0
             if (lane == 0) {
                 const size_t psym = unit + (s - 1) * n_units;
                 if (C::CL == 2) atomicMax(P.packed + psym, k);
@@ -575,22 +567,14 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 }
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o > best ? o : best;
-        }
+        best = warp_max_key(best);
         if (C::CL == 1 && lane == 0) sm.keys[s & 1][warp] = best;
     }
     if (C::CL == 2 && x_mine && n_mine > 0) finalize_prev(n_mine - 1);
     __syncthreads();
     if (C::CL == 1 && n_mine > 0 && warp == 0) {
         unsigned long long k = lane < C::NW ? sm.keys[(n_mine - 1) & 1][lane] : 0ull;
-#pragma unroll
-        for (int off = 8; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, k, off);
-            k = o > k ? o : k;
-        }
+        k = warp_max_key(k);      // lanes >= NW hold 0
         if (lane == 0) {
             const size_t psym = unit + (n_mine - 1) * n_units;
             if (C::CL == 2) atomicMax(P.packed + psym, k);

@@ -151,11 +151,7 @@ k1_sf10_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ mags) 
         s10_store2(t, slot, v);
         __syncthreads();
         unsigned long long best = s10_combine(t, slot, c);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o > best ? o : best;
-        }
+        best = warp_max_key(best);
         if (lane == 0) sm.keys[warp] = best;
         __syncthreads();
         if (t == 0) {

@@ -224,11 +224,7 @@ k1_sf7_warp_kernel(K1Args a, uint32_t *__restrict__ bins, float *__restrict__ ma
         other_q.x = __shfl_xor_sync(0xffffffffu, Pq.x, 1);
         other_q.y = __shfl_xor_sync(0xffffffffu, Pq.y, 1);
         unsigned long long best = w7_final(lane, c, own, other, Pq, other_q);
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const unsigned long long o = __shfl_xor_sync(0xffffffffu, best, off);
-            best = o > best ? o : best;
-        }
+        best = warp_max_key(best);
         if (lane == 0) {
             bins[sym] = key_idx(best);
             if (mags) mags[sym] = sqrtf(key_mag2(best));

@@ -156,5 +156,16 @@ LB_HD float key_mag2(unsigned long long k) {
     c.u = (uint32_t)(k >> 32);
     return c.f;
 }
+#ifdef __CUDACC__
+// Maximum key of the warp in every lane: two REDUX (the high words, then the low words of the lanes that hold the maximal
+// high word) instead of five dependent 64-bit shuffle + compare rounds (10 SHFL + 20 ALU; ~6 % of k1_rows<11>'s stall
+// samples sat on that chain, profiles/r2_k1_sf11.txt)
+LB_D unsigned long long warp_max_key(unsigned long long k) {
+    const uint32_t hi = (uint32_t)(k >> 32);
+    const uint32_t m = __reduce_max_sync(0xffffffffu, hi);
+    const uint32_t l = __reduce_max_sync(0xffffffffu, hi == m ? (uint32_t)k : 0u);
+    return ((unsigned long long)m << 32) | (unsigned long long)l;
+}
+#endif
 
 }  // namespace lb

@@ -118,14 +118,6 @@ LB_D float warp_sum(float v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-LB_D unsigned long long warp_max_key(unsigned long long k) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long t = __shfl_xor_sync(0xffffffffu, k, o);
-        k = t > k ? t : k;
-    }
-    return k;
-}
 
 // sum of up to 4 values over the CTA; result valid in every thread
 template <int NV>
