@@ -375,7 +375,7 @@ def check_frames(fr, pays_per_stream, k, n_streams):
     return expected, ok
 
 
-K1_KERNEL = {7: "k1_sf7_warp_kernel<12,2>", 8: "k1_group_kernel<8,6,2>", 9: "k1_group_kernel<9,3,2>", 10: "k1_sf10_kernel<2>",
+K1_KERNEL = {7: "k1_sf7_warp_kernel<12,2>", 8: "k1_group_kernel<8,6,2>", 9: "k1_group_kernel<9,3,2>", 10: "k1_sf10_kernel<3>",
              11: "k1_rows_kernel<11>", 12: "k1_rows_kernel<12>"}
 
 

@@ -35,6 +35,7 @@
 // non-GPU tests, with shared memory, tensor memory and the peer exchange modelled as plain arrays).
 #pragma once
 #include "k1_warp.cuh"
+#include "tmem.cuh"
 #ifdef __CUDACC__
 #include <cuda.h>      // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #endif
@@ -152,31 +153,6 @@ LB_HD float2 r_pass2_quirk(float2 (*g)[RCfg<SF>::A0], int E, float2 wb1, float2 
 }
 
 #ifdef __CUDACC__
-// ---- tensor memory ---------------------------------------------------------------------------------------------------------
-LB_D void tm_alloc(uint32_t *smem_dst) {      // one warp; R_TM_COLS columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(R_TM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-LB_D void tm_dealloc(uint32_t taddr) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(R_TM_COLS) : "memory");
-}
-LB_D void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-LB_D void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-LB_D void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-LB_D void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-// 16 consecutive columns of the thread's lane <-> 8 complex values
-LB_D void tm_st16(uint32_t taddr, const float2 *v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-                 ::"r"(taddr), "f"(v[0].x), "f"(v[0].y), "f"(v[1].x), "f"(v[1].y), "f"(v[2].x), "f"(v[2].y), "f"(v[3].x), "f"(v[3].y),
-                 "f"(v[4].x), "f"(v[4].y), "f"(v[5].x), "f"(v[5].y), "f"(v[6].x), "f"(v[6].y), "f"(v[7].x), "f"(v[7].y) : "memory");
-}
-LB_D void tm_ld16(uint32_t taddr, float2 *v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[2].x), "=f"(v[2].y), "=f"(v[3].x), "=f"(v[3].y),
-                   "=f"(v[4].x), "=f"(v[4].y), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[6].x), "=f"(v[6].y), "=f"(v[7].x), "=f"(v[7].y)
-                 : "r"(taddr) : "memory");
-}
-
 LB_D float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -276,7 +252,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 if (i < 8 || n_mine > 1) mbar_expect_tx(&sm.x_full[i], 2048u);          // phase 0 of the receive barriers (symbols 0 and 1)
         fence_mbar_init();
     }
-    if (warp == 0) tm_alloc(&sm.tm_base);
+    if (warp == 0) tm_alloc<R_TM_COLS>(&sm.tm_base);
     tm_fence_before();
     __syncthreads();
     tm_fence_after();
@@ -584,7 +560,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
     tm_fence_before();
     if (C::CL == 2) cluster_sync_all(); else __syncthreads();     // no CTA of the pair exits while the other may still store into it
     tm_fence_after();
-    if (warp == 0) tm_dealloc(sm.tm_base);
+    if (warp == 0) tm_dealloc<R_TM_COLS>(sm.tm_base);
 }
 #endif  // __CUDACC__
 

@@ -28,8 +28,8 @@ namespace lb {
 // scalar broadcasts {x,x}, the pair swaps {y,x} and whole-pair negations below into operand modifiers
 // (R.F32, .LO_HI, -R), so a complex multiply-add is two instructions.  The host build (CPU emulation
 // of the kernels for the non-GPU tests) uses the plain scalar formulas.
-#ifdef __CUDA_ARCH__
 typedef unsigned long long lb_u64;
+#ifdef __CUDA_ARCH__
 LB_D lb_u64 pk2(float lo, float hi) { lb_u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 LB_D float2 up2(lb_u64 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
 LB_D lb_u64 add2(lb_u64 a, lb_u64 b) { lb_u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
@@ -157,6 +157,34 @@ LB_HD float key_mag2(unsigned long long k) {
     return c.f;
 }
 #ifdef __CUDACC__
+// arg(x + i y) for the instantaneous-frequency passes (the reference's std::arg, lib/decoder_impl.cc:232-233, one per sample).
+// CUDA's atan2f is a rational approximation with two divisions and their slow-path checks: 65 instructions, 22 % of the
+// stream kernel's instructions (profiles/r2_rx_sf7_warp.txt).  This one: one IEEE division, t + t s P(s) with s = t^2 and a
+// degree-7 minimax P fitted to relative error (1.7e-8 before rounding), then the octant fix-ups: 26 instructions, measured
+// max error 1.8 ulp on 4e6 random points (CUDA documents 2 ulp for atan2f, so the two are interchangeable for parity:
+// both differ from glibc's result in the last bit on a fraction of the samples).  Zero, infinite and NaN inputs follow C99.
+LB_D float lb_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float q = __fdiv_rn(mn, mx);
+    if (mx == 0.0f) q = 0.0f;                                            // atan2(+-0, +-0)
+    if (mx == __int_as_float(0x7f800000)) q = mn == mx ? 1.0f : 0.0f;    // infinite operands
+    const float s = q * q;
+    float p = 0.0029206566978245974f;
+    p = fmaf(p, s, -0.01636778749525547f);
+    p = fmaf(p, s, 0.04321163520216942f);
+    p = fmaf(p, s, -0.07552195340394974f);
+    p = fmaf(p, s, 0.10665995627641678f);
+    p = fmaf(p, s, -0.14211052656173706f);
+    p = fmaf(p, s, 0.19993773102760315f);
+    p = fmaf(p, s, -0.33333152532577515f);
+    float r = fmaf(q * s, p, q);
+    if (ay > ax) r = 1.5707963705062866211f - r;
+    if (__float_as_int(x) < 0) r = 3.1415927410125732422f - r;
+    const float sum = ax + ay;
+    if (sum != sum) return sum;                                          // NaN in, NaN out
+    return copysignf(r, y);
+}
 // Maximum key of the warp in every lane: two REDUX (the high words, then the low words of the lanes that hold the maximal
 // high word) instead of five dependent 64-bit shuffle + compare rounds (10 SHFL + 20 ALU; ~6 % of k1_rows<11>'s stall
 // samples sat on that chain, profiles/r2_k1_sf11.txt)

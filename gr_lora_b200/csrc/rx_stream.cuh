@@ -169,9 +169,9 @@ LB_D void ifreq_block(const float2 *__restrict__ x, float *__restrict__ out, int
         const int i = base + threadIdx.x;
         const bool active = i < w;
         float p2 = 0.0f;
-        if (active) { const float2 s = x[i]; p2 = atan2f(s.y, s.x); }
+        if (active) { const float2 s = x[i]; p2 = lb_atan2f(s.y, s.x); }
         float p1 = __shfl_up_sync(0xffffffffu, p2, 1);
-        if (lane == 0 && active) { const float2 s = x[i - 1]; p1 = atan2f(s.y, s.x); }
+        if (lane == 0 && active) { const float2 s = x[i - 1]; p1 = lb_atan2f(s.y, s.x); }
         if (active) {
             // :236-237, float difference against the double M_PI, correction in double
             while (p2 - p1 > LB_PI_BELOW) p2 = (float)((double)p2 - 6.283185307179586);

@@ -22,7 +22,10 @@
 
 namespace lb {
 
-constexpr int RW_SPS = 1024, RW_N = 128, RW_WARPS = 9;       // 9 warps x ~213 registers fill the register file; 184 KiB of shared memory
+#ifndef LB_RW_WARPS
+#define LB_RW_WARPS 9
+#endif
+constexpr int RW_SPS = 1024, RW_N = 128, RW_WARPS = LB_RW_WARPS;       // 9 warps x ~213 registers fill the register file; 184 KiB of shared memory
 
 #ifdef __CUDACC__
 struct RWWarp {
@@ -34,7 +37,7 @@ struct RWSmem {
     float4 chirp[RW_SPS / 2];         // down-chirp, natural order
     float up_ifreq[RW_SPS];
     float down_ifreq[RW_SPS];
-    float up_ifreq_v[3 * RW_SPS];
+    float up_ifreq_v[3 * RW_SPS + 3 * RW_SPS / 32];   // padded: float n at n + (n >> 5)
     RWWarp w[RW_WARPS];
 };
 
@@ -44,33 +47,104 @@ LB_D void rw_load(const float2 *__restrict__ g, float2 *win, int n, int lane) {
     for (int k = lane; k < n; k += 32) win[k] = __ldcs(g + k);
 }
 
-// A3 instantaneous_frequency (:224-244) of win[0, w) (shared or global memory) into out[0, w); one atan2f per sample
+// A3 instantaneous_frequency (:224-244) of win[0, w) (shared or global memory) into out[0, w); one arg() per sample.
+// PAD: out is written with one unused float after every 32 (index j + (j >> 5)), the layout rw_sync_xcorr reads.
+template <bool PAD = false>
 LB_D void rw_ifreq(const float2 *win, float *out, int w, int lane) {
-    float a_cur;
-    { const float2 s = win[lane]; a_cur = atan2f(s.y, s.x); }
-    for (int base = 0; base < w; base += 32) {
-        const int nb = base + 32 + lane;
-        float a_nxt = 0.0f;
-        if (nb < w) { const float2 s = win[nb]; a_nxt = atan2f(s.y, s.x); }
-        const float n1 = __shfl_sync(0xffffffffu, a_cur, (lane + 1) & 31);
-        const float n2 = __shfl_sync(0xffffffffu, a_nxt, 0);
-        const int j = base + lane;                      // out[j] = wrap(arg x[j+1] - arg x[j])
-        if (j < w - 1) {
-            const float p1 = a_cur;
-            float p2 = lane == 31 ? n2 : n1;
-            // :236-237, float difference against the double M_PI, correction in double
-            while (p2 - p1 > LB_PI_BELOW) p2 = (float)((double)p2 - 6.283185307179586);
-            while (p2 - p1 < -LB_PI_BELOW) p2 = (float)((double)p2 + 6.283185307179586);
-            out[j] = p2 - p1;
+    // Four groups of 32 samples per iteration: their arg() chains (~26 dependent instructions each) are independent, and
+    // with two warps per scheduler the kernel lives on instruction-level parallelism (w is a multiple of 128).
+    // The wrap is two selects, not the reference's two while loops: both arguments are in [-pi, pi], so either loop runs at
+    // most once (a NaN fails both comparisons here as it fails both loop conditions there); the second test sees the
+    // result of the first correction, like the second loop.
+    float a[5];
+    { const float2 s = win[lane]; a[0] = lb_atan2f(s.y, s.x); }
+    for (int base = 0; base < w; base += 128) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int nb = base + 32 * (u + 1) + lane;
+            a[u + 1] = 0.0f;
+            if (nb < w) { const float2 s = win[nb]; a[u + 1] = lb_atan2f(s.y, s.x); }
         }
-        a_cur = a_nxt;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float n1 = __shfl_sync(0xffffffffu, a[u], (lane + 1) & 31);
+            const float n2 = __shfl_sync(0xffffffffu, a[u + 1], 0);
+            const int j = base + 32 * u + lane;             // out[j] = wrap(arg x[j+1] - arg x[j])
+            const float p1 = a[u];
+            const float p2 = lane == 31 ? n2 : n1;
+            // :236-237, float difference against the double M_PI (LB_PI_BELOW, lora_common.cuh), correction in double
+            float q2 = p2 - p1 > LB_PI_BELOW ? (float)((double)p2 - 6.283185307179586) : p2;
+            q2 = q2 - p1 < -LB_PI_BELOW ? (float)((double)q2 + 6.283185307179586) : q2;
+            if (j < w - 1) out[PAD ? j + (j >> 5) : j] = q2 - p1;
+        }
+        a[0] = a[4];
     }
     __syncwarp();
-    if (lane == 0) out[w - 1] = out[w - 2];
+    if (lane == 0) out[PAD ? w - 1 + ((w - 1) >> 5) : w - 1] = out[PAD ? w - 2 + ((w - 2) >> 5) : w - 2];
     __syncwarp();
 }
 
-// A6 fine_sync (:300-338) on ifq[0, sps): lane-strided products + butterfly sum per lag, as fine_sync_block does
+// A9 sliding_norm_cross_correlate_upchirp (:392-413): c[lag] = sum_k f[lag + k] up[k], lag = 0 .. sps - 1, k = 0 .. sps - 2,
+// every sum in k order with separate multiply and add like the reference's scalar dot product (cross_correlate_ifreq_fast ->
+// volk_32f_x2_dot_prod_32f, :259-263), so the first maximum is the reference's sample index.
+//
+// Lane l owns the 32 consecutive lags 32 l + j.  At step k it needs f[32 l + k + j], j = 0..31: a window that slides by one
+// float per step, so it lives in registers (V, indexed modulo 64: two blocks of 32 steps, PAR = block parity, make every
+// register index a compile-time number) and ONE new float is loaded per step; the first version fetched all 32 from shared
+// memory, 97 instructions per step and 22 % of the kernel's instructions.  Per step: 32 FMUL, 16 FADD2 (add.rn.f32x2 on
+// accumulator pairs), one LDS = 49 instructions.  The products stay scalar on purpose: ptxas contracts mul.rn.f32x2 +
+// add.rn.f32x2 into FFMA2 despite the explicit rounding (checked on the SASS, also with -fmad=false), which would round
+// once where the reference rounds twice; a scalar FMUL feeding a packed add is left alone.
+// f is read from the padded layout (33 floats per 32): the lanes are 33 floats apart, conflict-free.
+constexpr int RW_XC_LA = 8;                                           // a float is loaded this many steps before its first use
+LB_D int rw_xc_off(int n) { return n + (n >> 5); }                    // padded offset of float n of a lane's row sequence
+template <int PAR>
+LB_D void rw_xc_block(float (&V)[64], lb_u64 (&c2)[16], const float *rows, const float *u, bool short_block) {
+#ifdef __CUDA_ARCH__                                                  // (the packed helpers exist in the device pass only)
+    float4 uq = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int t = 0; t < 32; t++) {
+        if (t == 31 && short_block) continue;                         // k stops at sps - 2 (last step of the last block)
+        const int T = 32 * PAR + t;
+        // V[T + 32 + LA] (first used RW_XC_LA steps from now) replaces a float whose last use is long past
+        V[(T + 32 + RW_XC_LA) & 63] = rows[rw_xc_off(32 + RW_XC_LA + t)];
+        if ((t & 3) == 0) uq = *reinterpret_cast<const float4 *>(u + t);
+        const float ut = (t & 3) == 0 ? uq.x : (t & 3) == 1 ? uq.y : (t & 3) == 2 ? uq.z : uq.w;
+#pragma unroll
+        for (int i = 0; i < 16; i++)
+            c2[i] = add2(c2[i], pk2(__fmul_rn(V[(2 * i + T) & 63], ut), __fmul_rn(V[(2 * i + 1 + T) & 63], ut)));
+    }
+#endif
+}
+// f: padded instantaneous frequency of two windows; up: up_ifreq (16-byte aligned).  Returns the warp's best key (0: no c > 0).
+LB_D unsigned long long rw_sync_xcorr(const float *f, const float *up, int lane) {
+    unsigned long long best = 0ull;
+#ifdef __CUDA_ARCH__
+    float V[64];
+    lb_u64 c2[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) c2[i] = pk2(0.0f, 0.0f);
+    const float *rows = f + 33 * lane;                                // float n of block m: rows[33 m + rw_xc_off(n)]
+#pragma unroll
+    for (int n = 0; n < 64; n++) V[n] = n < 32 + RW_XC_LA ? rows[rw_xc_off(n)] : 0.0f;
+    for (int m2 = 0; m2 < RW_SPS / 64; m2++) {
+        rw_xc_block<0>(V, c2, rows + 33 * (2 * m2), up + 64 * m2, false);
+        rw_xc_block<1>(V, c2, rows + 33 * (2 * m2 + 1), up + 64 * m2 + 32, m2 == RW_SPS / 64 - 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float2 c = up2(c2[i]);
+        const unsigned long long k0 = corr_key(c.x, (uint32_t)(32 * lane + 2 * i)), k1 = corr_key(c.y, (uint32_t)(32 * lane + 2 * i + 1));
+        best = k0 > best ? k0 : best;
+        best = k1 > best ? k1 : best;
+    }
+    best = warp_max_key(best);
+#endif
+    return best;
+}
+
+// A6 fine_sync (:300-338) on ifq[0, sps), the three-lag search of a payload symbol: lane-strided products + butterfly sum per
+// lag, as fine_sync_block does.  up_v is the padded table.
 LB_D int rw_fine_sync(const float *ifq, const float *up_v, int bin_idx, int search, int lane) {
     const int shift_ref = (bin_idx + 1) * 8;                      // :301, decim = 8
     const int last = 3 * RW_SPS - 1;
@@ -82,7 +156,7 @@ LB_D int rw_fine_sync(const float *ifq, const float *up_v, int bin_idx, int sear
         for (int k = lane; k < RW_SPS; k += 32) {
             int idx = start + k;
             idx = idx < 0 ? 0 : (idx > last ? last : idx);        // defined over-read (oracle D1)
-            c = fmaf(ifq[k], up_v[idx], c);
+            c = fmaf(ifq[k], up_v[idx + (idx >> 5)], c);
         }
         c = warp_sum(c);
         const unsigned long long key = corr_key(c, (uint32_t)li);
@@ -90,6 +164,47 @@ LB_D int rw_fine_sync(const float *ifq, const float *up_v, int bin_idx, int sear
     }
     const int lag = best ? (int)key_idx(best) - (search - 1) : 0;
     return -lag;                                                  // :321
+}
+
+// A6 fine_sync (:300-338) for the preamble call fine_sync(ifreq, -1, decim * 4) (:803): 63 lags, shift = li - 31, of
+//     c[li] = sum_k ifq[k] up_v[sps - 31 + li + k],  k = 0 .. sps - 1        (no index leaves the table: no clamping).
+// One lag at a time that is 2 loads per product (the first version: 12 000 instructions per call, 14 % of the kernel's
+// instructions).  Here lane l owns the products of k = 32 l .. 32 l + 31 for ALL lags: the table window it needs slides
+// by one float per k, so it lives in registers (one new float per step) next to the 63 accumulators -- 65 instructions per
+// step.  The 32 partial sums of every lag are then added in lane order through a 32 x 63 scratch array.
+// ifq_p and up_vp are padded (float n at n + (n >> 5)): the lanes' rows are 33 floats apart, conflict-free.
+constexpr int RW_FS_LA = 6;
+LB_D int rw_fine_sync63(const float *ifq_p, const float *up_vp, float *scratch, int lane) {
+    constexpr int first = RW_SPS - 31;                                // table index of (li = 0, k = 0); first % 32 == 1
+    const float *a = ifq_p + 33 * lane;
+    const float *w = up_vp + (first + (first >> 5)) + 33 * lane;      // W[n] = table[first + 32 lane + n] = w[n + ((n + 1) >> 5)]
+    float c[63], W[96];
+#pragma unroll
+    for (int li = 0; li < 63; li++) c[li] = 0.0f;
+#pragma unroll
+    for (int n = 0; n < 96; n++) W[n] = n < 62 + RW_FS_LA ? w[n + ((n + 1) >> 5)] : 0.0f;
+#pragma unroll
+    for (int kk = 0; kk < 32; kk++) {
+        if (kk + 62 + RW_FS_LA < 94) W[kk + 62 + RW_FS_LA] = w[kk + 62 + RW_FS_LA + ((kk + 63 + RW_FS_LA) >> 5)];
+        const float ak = a[kk];
+#pragma unroll
+        for (int li = 0; li < 63; li++) c[li] = fmaf(ak, W[kk + li], c[li]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int li = 0; li < 63; li++) scratch[63 * lane + li] = c[li];
+    __syncwarp();
+    float s0 = 0.0f, s1 = 0.0f;                                       // lags lane and lane + 32
+#pragma unroll
+    for (int l = 0; l < 32; l++) {
+        s0 += scratch[63 * l + lane];
+        if (lane < 31) s1 += scratch[63 * l + lane + 32];
+    }
+    __syncwarp();
+    const unsigned long long k0 = corr_key(s0, (uint32_t)lane), k1 = lane < 31 ? corr_key(s1, (uint32_t)(lane + 32)) : 0ull;
+    const unsigned long long best = warp_max_key(k0 > k1 ? k0 : k1);
+    const int lag = best ? (int)key_idx(best) - 31 : 0;
+    return -lag;                                                      // :321
 }
 
 template <bool FFT>
@@ -102,7 +217,7 @@ rx_warp_kernel(RxParams p) {
 
     for (int i = threadIdx.x; i < RW_SPS / 2; i += RW_WARPS * 32) sm.chirp[i] = k1_ld_table4(p.down + 2 * i);
     for (int i = threadIdx.x; i < RW_SPS; i += RW_WARPS * 32) { sm.up_ifreq[i] = __ldg(p.up_ifreq + i); sm.down_ifreq[i] = __ldg(p.down_ifreq + i); }
-    for (int i = threadIdx.x; i < 3 * RW_SPS; i += RW_WARPS * 32) sm.up_ifreq_v[i] = __ldg(p.up_ifreq_v + i);
+    for (int i = threadIdx.x; i < 3 * RW_SPS; i += RW_WARPS * 32) sm.up_ifreq_v[i + (i >> 5)] = __ldg(p.up_ifreq_v + i);
     __syncthreads();
 
     const uint32_t local = blockIdx.x * RW_WARPS + warp;          // stream of this launch
@@ -165,25 +280,10 @@ rx_warp_kernel(RxParams p) {
             break;
         }
         case LORA_B200_SYNC: {                                    // :770-783, A9 :392-413
-            rw_ifreq(x, ifq, 2 * sps, lane);                     // straight from global memory: every sample is touched once
-            // lag i = lane + 32 j, j = 0..31: products added in index order with separate multiply and add, like the
-            // reference's scalar dot product (cross_correlate_ifreq_fast -> volk_32f_x2_dot_prod_32f, :259-263)
-            float c[32];
-#pragma unroll
-            for (int j = 0; j < 32; j++) c[j] = 0.0f;
-            const float *f0 = ifq + lane;
-            for (int k = 0; k < sps - 1; k++) {
-                const float u = sm.up_ifreq[k];
-#pragma unroll
-                for (int j = 0; j < 32; j++) c[j] = __fadd_rn(c[j], __fmul_rn(f0[32 * j + k], u));
-            }
-            unsigned long long best = 0ull;
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const unsigned long long key = corr_key(c[j], (uint32_t)(lane + 32 * j));
-                best = key > best ? key : best;
-            }
-            best = warp_max_key(best);
+            // straight from global memory (every sample is touched once) into the padded layout, over win and the head of ifq
+            float *fpad = reinterpret_cast<float *>(ws.win);
+            rw_ifreq<true>(x, fpad, 2 * sps, lane);
+            const unsigned long long best = rw_sync_xcorr(fpad, sm.up_ifreq, lane);
             metric = best ? key_mag2(best) : 0.0f;
             consumed = best ? (int)key_idx(best) : 0;             // :780 consume_each(i)
             next_state = LORA_B200_FIND_SFD;
@@ -201,17 +301,17 @@ rx_warp_kernel(RxParams p) {
         case LORA_B200_FIND_SFD: {                                // :785-818, A10
             rw_load(x, win, sps, lane);
             __syncwarp();
-            rw_ifreq(win, ifq, sps, lane);
+            rw_ifreq<true>(win, ifq, sps, lane);                  // padded: float i at i + (i >> 5) = lane + 33 j for i = lane + 32 j
             const int to_idx = sps - 1;
             float s1 = 0.f;
 #pragma unroll 8
-            for (int i = lane; i < to_idx; i += 32) s1 += ifq[i];
+            for (int i = lane, ip = lane; i < to_idx; i += 32, ip += 33) s1 += ifq[ip];
             s1 = warp_sum(s1);
             const float average = s1 / (float)to_idx;             // :286
             float q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
-            for (int i = lane; i < to_idx; i += 32) {
-                const float t = ifq[i] - average;
+            for (int i = lane, ip = lane; i < to_idx; i += 32, ip += 33) {
+                const float t = ifq[ip] - average;
                 q0 = fmaf(t, t, q0);                              // stddev :415-425
                 q1 = fmaf(t, sm.down_ifreq[i] - p.down_ifreq_avg, q1);
             }
@@ -219,7 +319,7 @@ rx_warp_kernel(RxParams p) {
             const float sd = sqrtf(q0 / (float)to_idx) * p.down_ifreq_sd;   // :288-289
             const float cc = q1 / sd / (float)to_idx;             // :291-295
             const bool up_again = !(cc > 0.96f) && (cc < -0.97f);
-            if (up_again) fine = rw_fine_sync(ifq, sm.up_ifreq_v, -1, 32, lane);   // :803, decim * 4
+            if (up_again) fine = rw_fine_sync63(ifq, sm.up_ifreq_v, reinterpret_cast<float *>(ws.win), lane);   // :803, fine_sync(ifreq, -1, decim * 4)
             metric = cc;
             if (cc > 0.96f) {
                 next_state = LORA_B200_PAUSE;                     // :799

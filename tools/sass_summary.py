@@ -11,7 +11,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 FAMILIES = ["UBLKCP", "UTMALDG", "SYNCS", "LDTM", "STTM", "FFMA2", "FADD2", "FMUL2", "FFMA", "LDS", "STS", "LDG", "SHFL", "BAR", "MEMBAR", "UTCALLOC", "UTCMMA", "HMMA"]
-DEFAULT = ["k1_sf7_warp_kernelILi12ELi2E", "k1_group_kernelILi8ELi6ELi2E", "k1_group_kernelILi9ELi3ELi2E", "k1_sf10_kernelILi2E",
+DEFAULT = ["k1_sf7_warp_kernelILi12ELi2E", "k1_group_kernelILi8ELi6ELi2E", "k1_group_kernelILi9ELi3ELi2E", "k1_sf10_kernelILi3E",
            "k1_rows_kernelILi11E", "k1_rows_kernelILi12E", "rx_stream_kernelILi7ELb0E", "rx_stream_kernelILi7ELb1E", "k8_frames_kernel",
            "chan_fir_kernel", "sc16_to_cf32_kernel", "k1_finalize_kernel"]
 
