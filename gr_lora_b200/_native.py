@@ -59,6 +59,7 @@ SIGNATURES = {
     "lora_b200_work_batch_sc16": (_i, [_vp, _vp, C.c_float, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_frames_last": (_sz, [_vp, C.POINTER(_vp)]),
     "lora_b200_stream_state": (_i, [_vp, _u32]),
+    "lora_b200_reset": (_i, [_vp]),
     "lora_b200_set_cfo_estimate": (_i, [_vp, _i]),
     "lora_b200_last_cfo": (_i, [_vp, _u32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "lora_b200_stdout_last": (_i, [_vp, _u32, C.c_char_p, _sz]),

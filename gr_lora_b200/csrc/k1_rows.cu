@@ -84,6 +84,31 @@ int launch(int device, int n_sms, const float2 *iq, const float2 *chirp, const f
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     RCU(cudaLaunchKernelEx(&cfg, k1_rows_kernel<SF>, P));
+#ifdef LB_ROWS_TIMING
+    {   // diagnosis build: mean cycles per symbol and warp class spent in each wait
+        RCU(cudaStreamSynchronize(st));
+        static unsigned int h[160 * 16 * 8];
+        RCU(cudaMemcpyFromSymbol(h, r_timing_dev, sizeof h));
+        const char *names[6] = {"x_full", "x_free", "sym_full", "sym_late", "barrier", "-"};
+        for (int rank = 0; rank < C::CL; rank++)
+            for (int half = 0; half < 2; half++) {
+                double acc[7] = {0, 0, 0, 0, 0, 0, 0}, nsym = 0;
+                int cnt = 0;
+                for (unsigned b = 0; b < cfg.gridDim.x; b++) {
+                    if ((int)(b % C::CL) != rank) continue;
+                    for (int w = 8 * half; w < 8 * half + 8; w++) {
+                        const unsigned int *o = h + (b * 16 + w) * 8;
+                        for (int i = 0; i < 7; i++) acc[i] += o[i];
+                        nsym += o[7];
+                        cnt++;
+                    }
+                }
+                fprintf(stderr, "rows<%d> rank %d warps %d-%d: %.0f cycles/symbol;", SF, rank, 8 * half, 8 * half + 7, acc[6] / nsym);
+                for (int i = 0; i < 5; i++) fprintf(stderr, " %s %.0f", names[i], acc[i] / nsym);
+                fprintf(stderr, "\n");
+            }
+    }
+#endif
     return 0;
 }
 

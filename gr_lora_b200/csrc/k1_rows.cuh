@@ -204,6 +204,19 @@ LB_D void tma_rows_2d(void *dst_smem, const void *tmap, int c0, int c1, uint64_t
                  ::"r"(smem_u32(dst_smem)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
+// Diagnosis build (-DLB_ROWS_TIMING, tools only): cycles every warp spends in each kind of wait, read back by the launcher.
+#ifdef LB_ROWS_TIMING
+__device__ unsigned int r_timing_dev[160 * 16 * 8];
+#define RT_DECL unsigned int rt_acc[6] = {0, 0, 0, 0, 0, 0}; const unsigned int rt_start = (unsigned int)clock();
+#define RT(i, stmt) do { const unsigned int rt_t0 = (unsigned int)clock(); stmt; rt_acc[i] += (unsigned int)clock() - rt_t0; } while (0)
+#define RT_FLUSH do { if (lane == 0) { unsigned int *o = r_timing_dev + (blockIdx.x * 16 + warp) * 8; for (int i = 0; i < 6; i++) o[i] = rt_acc[i]; \
+                                    o[6] = (unsigned int)clock() - rt_start; o[7] = (unsigned int)n_mine; } } while (0)
+#else
+#define RT_DECL
+#define RT(i, stmt) stmt
+#define RT_FLUSH
+#endif
+
 template <int SF>
 struct RSmem {
     float4 slots[RCfg<SF>::NSLOT][RCfg<SF>::ROW_F4];
@@ -331,12 +344,13 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
     // pass 2: unit = K ^ m with K = (a0, e) a compile-time number and m = (the lane pair's bit) ^ swizzle(kb) a lane constant;
     // only the low three unit bits meet m, so 4 XORed addresses per symbol cover all 16 loads
     const uint32_t m2 = (uint32_t)((SF == 11 ? 2 * (lane & 1) : (lane & 1)) ^ r_swz<SF>(lane >> 1)) * 16u + (uint32_t)(lane >> 1) * 512u;
+    RT_DECL
     // SF12 exchange roles: warp pair x_i; this CTA finishes the bins of rows kc with (kc >> 3) == rank
     const int x_i = warp & 7;
     const bool x_mine = C::CL == 2 && (uint32_t)(warp >> 3) == rank;
     auto finalize_prev = [&](size_t sp) {          // receiver warps: own sums (tensor memory) + the peer's (recv) of symbol sp -> argmax
         const int xb = (int)(sp & 1) * 8 + x_i;
-        mbar_wait(&sm.x_full[xb], (uint32_t)((sp >> 1) & 1));
+        RT(0, mbar_wait(&sm.x_full[xb], (uint32_t)((sp >> 1) & 1)));
         float2 o[8];
         tm_ld16(tm_lane + (uint32_t)(R_TM_STASH + 16 * (warp >> 2)), o);
         const float4 *rblk = reinterpret_cast<const float4 *>(&sm.recv[xb * 256]);
@@ -378,14 +392,14 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         }
         uint32_t rowaddr;
         { int t = base + warp; if (t >= C::NSLOT) t -= C::NSLOT; rowaddr = slots0 + (uint32_t)t * C::ROW_BYTES; }
-        mbar_wait(&sm.sym_full[s % R_NSYM_BAR], (uint32_t)((s / R_NSYM_BAR) & 1));
+        RT(2, mbar_wait(&sm.sym_full[s % R_NSYM_BAR], (uint32_t)((s / R_NSYM_BAR) & 1)));
 
         // ---- pass 0: radix 16 over the rows, warp = a1 block -----------------------------------------------------------
         {
             float2 v0[16], v1[16], tw[16];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                if (4 * q == RLate<SF>::EARLY) mbar_wait(&sm.sym_late[s % R_NSYM_BAR], (uint32_t)((s / R_NSYM_BAR) & 1));
+                if (4 * q == RLate<SF>::EARLY) RT(3, mbar_wait(&sm.sym_late[s % R_NSYM_BAR], (uint32_t)((s / R_NSYM_BAR) & 1)));
                 float2 ch[8];
                 tm_ld16(tm_lane + (uint32_t)(R_TM_CHIRP + 64 * (warp >> 2) + 16 * q), ch);
                 float4 xv[4];
@@ -410,7 +424,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
                 sts128(st0 + gb[kc >> 2] + (uint32_t)(kc & 3) * C::ROW_BYTES, make_float4(v0[br].x, v0[br].y, v1[br].x, v1[br].y));
             }
         }
-        __syncthreads();
+        RT(4, __syncthreads());
         // result of the previous symbol (its keys were complete before this barrier)
         if (C::CL == 1 && s > 0 && warp == 0) {
             unsigned long long k = lane < C::NW ? sm.keys[(s - 1) & 1][lane] : 0ull;
@@ -446,8 +460,14 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         }
         __syncwarp();
         // ---- pass 2: radix A0 over a0, branch sum, argmax ---------------------------------------------------------------
-        // SF12: the sums of the PREVIOUS symbol are completed first -- the peer's half has had a whole symbol time to arrive,
-        // so the wait below does not stall (second capture: 9 % of all samples waited for the peer's block of the same symbol)
+        // SF12: the sums of the PREVIOUS symbol are completed first (the peer's half has had a symbol time to arrive).
+        // Measured alternatives (tools/k1_ab.py, LB_ROWS_TIMING build): merging the same symbol's sums at the end of pass 2
+        // 0.43 (9 % of samples in the wait); this 0.46 although the receivers still wait ~4 300 of 12 750 cycles for the 128
+        // remote st.async transactions of a block; one cp.async.bulk per block instead (no wait, but 32 KiB for send + receive
+        // buffers) 0.42; this merge moved behind the pass-2 arithmetic 0.41.  The last two remove the wait and lose: with it the
+        // receiving half of the warps runs a third of a symbol behind the sending half, so the TMA refills and the FMA-heavy
+        // and LSU-heavy phases of the two halves interleave instead of colliding; what bounds SF12 is the refill of the last 8
+        // rows (sym_late: 2 100 - 3 300 cycles per symbol in every variant), i.e. 24 slots = 1.5 symbols of shared memory.
         if (C::CL == 2 && x_mine && s > 0) finalize_prev(s - 1);
         unsigned long long best = 0ull;
         {
@@ -517,13 +537,15 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
             }
             if (C::CL == 2) {
                 // bins of rows kc < 8 are finished by CTA 0, kc >= 8 by CTA 1.  The other CTA sends its partial sums straight
-                // from registers through the async proxy (st.async ... mbarrier::complete_tx on the peer's barrier): no staging,
-                // no cluster-scope fence or acquire (the first version's DSMEM stores + fence.acq_rel.cluster +
-                // try_wait.acquire.cluster compiled to MEMBAR.ALL.GPU + ERRBAR + CCTL.IVALL: 30 % of all stall samples).
+                // from registers through the async proxy (st.async ... mbarrier::complete_tx on the peer's barrier): no staging
+                // buffer (its 16 KiB are the second receive buffer), no cluster-scope fence or acquire (the first version's
+                // DSMEM stores + fence.acq_rel.cluster + try_wait.acquire.cluster compiled to MEMBAR.ALL.GPU + ERRBAR +
+                // CCTL.IVALL: 30 % of all stall samples).  The 128 remote transactions per block take ~4 000 cycles to land
+                // (LB_ROWS_TIMING build), which the one-symbol deferral of the merge hides.
                 if (quirk_warp && lane == 1) f[0] = cadd(f[0], tq);      // both evaluations of bin N/2 are additive
                 if (!x_mine) {
                     const int xb = (int)(s & 1) * 8 + x_i;
-                    if (s > 1) mbar_wait(&sm.x_free[xb], (uint32_t)(((s >> 1) - 1) & 1));     // the peer has consumed symbol s - 2 (a symbol time ago)
+                    if (s > 1) RT(1, mbar_wait(&sm.x_free[xb], (uint32_t)(((s >> 1) - 1) & 1)));     // the peer has consumed symbol s - 2 (a symbol time ago)
                     const uint32_t dst = map_to_peer(smem_u32(&sm.recv[xb * 256]), peer) + (uint32_t)lane * 16u;
                     const uint32_t bar = map_to_peer(smem_u32(&sm.x_full[xb]), peer);
 #pragma unroll
@@ -547,6 +569,7 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
         if (C::CL == 1 && lane == 0) sm.keys[s & 1][warp] = best;
     }
     if (C::CL == 2 && x_mine && n_mine > 0) finalize_prev(n_mine - 1);
+    RT_FLUSH;
     __syncthreads();
     if (C::CL == 1 && n_mine > 0 && warp == 0) {
         unsigned long long k = lane < C::NW ? sm.keys[(n_mine - 1) & 1][lane] : 0ull;

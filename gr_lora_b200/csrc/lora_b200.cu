@@ -90,6 +90,7 @@ struct lora_b200_decoder {
     cudaStream_t rx_stream = nullptr, rx_stream2 = nullptr;
     cudaEvent_t rx2_done = nullptr, rx_begin_ev = nullptr;
     RxStreamState *d_states = nullptr;
+    uint8_t phdr1_init = 0;
     float *d_scratch = nullptr;
     unsigned long long *d_consumed = nullptr;
     RxFrameRec *d_frames = nullptr;
@@ -493,6 +494,19 @@ extern "C" {
 const char *lora_b200_last_error(void) { return g_err.c_str(); }
 int lora_b200_abi_version(void) { return LORA_B200_ABI_VERSION; }
 
+// decoder_impl's members as the constructor leaves them (:55-66), for every stream
+static cudaError_t init_states(lora_b200_decoder *d) {
+    const uint32_t ns = d->cfg.n_streams;
+    std::vector<RxStreamState> init(ns);
+    memset(init.data(), 0, sizeof(RxStreamState) * ns);
+    for (auto &s : init) {
+        s.state = LORA_B200_DETECT;                                      // :55
+        s.snr = 1.0f;                                                    // reference leaves d_snr uninitialised (oracle D4)
+        s.phdr[1] = d->phdr1_init;
+    }
+    return cudaMemcpy(d->d_states, init.data(), sizeof(RxStreamState) * ns, cudaMemcpyHostToDevice);
+}
+
 lora_b200_decoder *lora_b200_create(const lora_b200_config *cfg) {
     if (!cfg) { fail(LORA_B200_EINVAL, "null config"); return nullptr; }
     if (cfg->sf < 6 || cfg->sf > 13) {            // decoder_impl.cc:57-61 (the reference prints this and exit(1)s)
@@ -560,16 +574,8 @@ lora_b200_decoder *lora_b200_create(const lora_b200_config *cfg) {
     const uint32_t ns = d->cfg.n_streams;
     if ((e = cudaStreamCreateWithFlags(&d->rx_stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaMalloc(&d->d_states, sizeof(RxStreamState) * ns)) != cudaSuccess) return bail("cudaMalloc states", e);
-    {
-        std::vector<RxStreamState> init(ns);
-        memset(init.data(), 0, sizeof(RxStreamState) * ns);
-        for (auto &s : init) {
-            s.state = LORA_B200_DETECT;                                  // :55
-            s.snr = 1.0f;                                                // reference leaves d_snr uninitialised (oracle D4)
-            s.phdr[1] = (uint8_t)((cr3 << 5) | ((cfg->crc ? 1u : 0u) << 4));   // :72-73
-        }
-        if ((e = cudaMemcpy(d->d_states, init.data(), sizeof(RxStreamState) * ns, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("init states", e);
-    }
+    d->phdr1_init = (uint8_t)((cr3 << 5) | ((cfg->crc ? 1u : 0u) << 4));       // :72-73
+    if ((e = init_states(d)) != cudaSuccess) return bail("init states", e);
     const size_t scr_per = 2 * (size_t)d->sps + d->n_bins;
     if ((e = cudaMalloc(&d->d_scratch, sizeof(float) * scr_per * ns)) != cudaSuccess) return bail("cudaMalloc scratch", e);
     if ((e = cudaMalloc(&d->d_consumed, sizeof(unsigned long long) * ns)) != cudaSuccess) return bail("cudaMalloc consumed", e);
@@ -839,12 +845,14 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
     int rc = ensure_stage(d, n_items * ns, false, sc16);
     if (rc) return rc;
     if (!d->copy_streams[0]) CU(cudaStreamCreateWithFlags(&d->copy_streams[0], cudaStreamNonBlocking));
-    // groups: one launch each; a group should fill the machine at least once (rx_warp_kernel: 9 streams per CTA, one CTA per
+    // groups: one launch each; a group should fill the machine about once (rx_warp_kernel: RW_WARPS streams per CTA, one CTA per
     // SM; rx_stream_kernel: one stream per CTA, two CTAs per SM), small batches stay whole.  Consecutive groups run on two
     // alternating compute streams so that the tail of one launch overlaps the head of the next.
     const bool warp_kernel = d->cfg.sf == 7 && d->sps == (uint32_t)RW_SPS;
     const uint32_t per_wave = (uint32_t)d->n_sms * (warp_kernel ? (uint32_t)RW_WARPS : 2u);
-    const uint32_t n_groups = std::max<uint32_t>(1u, std::min<uint32_t>(8u, ns / per_wave));
+    // (a group of per_wave + 1 streams would take two waves: round the number of groups UP, so that the last group -- the
+    // only one whose state machine is not hidden under a copy -- is a single wave)
+    const uint32_t n_groups = std::max<uint32_t>(1u, std::min<uint32_t>(8u, (ns + per_wave - 1) / per_wave));
     const uint32_t gs = (ns + n_groups - 1) / n_groups;
     if (!d->rx_stream2) {
         CU(cudaStreamCreateWithFlags(&d->rx_stream2, cudaStreamNonBlocking));
@@ -865,8 +873,11 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
         cudaStream_t xs = (g & 1) ? d->rx_stream2 : d->rx_stream;
         const uint8_t *src = (const uint8_t *)iq + (size_t)s0 * stride_items * elem;
         void *dst = sc16 ? (void *)(d->d_stage16 + (size_t)s0 * n_items) : (void *)(d->d_stage + (size_t)s0 * n_items);
-        CU(cudaMemcpy2DAsync(dst, elem * n_items, src, elem * stride_items, elem * n_items, cnt,
-                             host_ptr ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
+        if (stride_items == n_items)                                  // dense rows: one linear copy (the 2-D form is for strided captures)
+            CU(cudaMemcpyAsync(dst, src, elem * n_items * cnt, host_ptr ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
+        else
+            CU(cudaMemcpy2DAsync(dst, elem * n_items, src, elem * stride_items, elem * n_items, cnt,
+                                 host_ptr ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
         CU(cudaEventRecord(d->stage_events[g], cs));
         CU(cudaStreamWaitEvent(xs, d->stage_events[g], 0));
         if (sc16) {
@@ -891,6 +902,19 @@ int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, s
 int lora_b200_work_batch_sc16(lora_b200_decoder *d, const void *iq_sc16, float scale, size_t n_items, size_t stride_items,
                               int host_ptr, size_t *consumed, lora_b200_frame_cb cb, void *user) {
     return work_batch_any(d, iq_sc16, sizeof(short2), scale, n_items, stride_items, host_ptr, consumed, cb, user);
+}
+
+int lora_b200_reset(lora_b200_decoder *d) {
+    if (!d) return fail(LORA_B200_EINVAL, "null argument");
+    CU(cudaSetDevice(d->device));
+    CU(cudaStreamSynchronize(d->rx_stream));
+    if (d->rx_stream2) CU(cudaStreamSynchronize(d->rx_stream2));
+    CU(init_states(d));
+    CU(cudaMemset(d->d_consumed, 0, sizeof(unsigned long long) * d->cfg.n_streams));
+    if (d->d_trace_n) CU(cudaMemset(d->d_trace_n, 0, sizeof(uint32_t) * d->cfg.n_streams));
+    d->h_sorted.clear();
+    for (auto &so : d->stdout_last) so.clear();
+    return LORA_B200_OK;
 }
 
 int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream) {

@@ -6,14 +6,20 @@
 // samples = 32 per lane, which is exactly the shape of the SF7 K1 warp kernel (k1_warp.cuh).  Here a warp owns a stream:
 //   * the window (<= 2 sps samples, 16 KiB), its instantaneous frequency (8 KiB) and the decoder_impl members
 //     (RxStreamState) live in the warp's own shared memory; the four tables (down-chirp, up / down ifreq, 3 x up ifreq)
-//     are shared by the CTA's 7 warps; nothing but the IQ itself is read from global memory inside the loop;
+//     are shared by the CTA's 10 warps; nothing but the IQ itself is read from global memory inside the loop;
 //   * every step of work() (lib/decoder_impl.cc:740-903) is warp wide with __syncwarp() only: detect_preamble_autocorr,
 //     sliding_norm_cross_correlate_upchirp, detect_downchirp, fine_sync, max_frequency_gradient_idx, determine_energy;
 //     the FFT demodulator is the k1_warp.cuh pipeline on the window in place;
-//   * the sliding correlation of the SYNC step (:399-413), sps lags x (sps - 1) products, keeps 32 lags per lane in
-//     registers and adds the products of every lag IN INDEX ORDER with separate multiply and add -- the order of the
-//     reference's scalar dot product -- so the chosen index is the oracle's bit for bit (the CTA kernel's tree sum may pick
-//     the neighbouring sample on ties); the three-lag fine_sync keeps the CTA kernel's lane-strided order.
+//   * the sliding correlation of the SYNC step (:399-413), sps lags x (sps - 1) products, keeps 32 consecutive lags per lane
+//     in registers together with the sliding window of the instantaneous frequency they need (one new float per step), and
+//     adds the products of every lag IN INDEX ORDER with separate multiply and add -- the order of the reference's scalar
+//     dot product -- so the chosen index is the oracle's bit for bit (the CTA kernel's tree sum may pick the neighbouring
+//     sample on ties).  The 63-lag fine_sync of the preamble uses the same register-resident window per
+//     lane over a block of 32 products; the three-lag fine_sync of a payload symbol keeps the CTA kernel's lane-strided
+//     order.  arg() is lb_atan2f (lora_common.cuh), four groups of 32 samples at a time.
+//   * what bounds it: two warps per scheduler, every one a chain of dependent steps (ncu, profiles/r2_rx_sf7_warp.txt:
+//     issue slots 35 % active, stall "wait" 38 %); the listed changes took 4096 streams x 256 windows from 2.24e7 to
+//     2.64e7 windows/s.
 // Same observable behaviour as rx_stream_kernel: frames, consume amounts, per-step trace.  Other SFs and sample rates use
 // rx_stream_kernel.
 #pragma once
@@ -23,9 +29,11 @@
 namespace lb {
 
 #ifndef LB_RW_WARPS
-#define LB_RW_WARPS 9
+#define LB_RW_WARPS 10
 #endif
-constexpr int RW_SPS = 1024, RW_N = 128, RW_WARPS = LB_RW_WARPS;       // 9 warps x ~213 registers fill the register file; 184 KiB of shared memory
+// 10 warps: three per scheduler on two of the four (168 registers each), 198 KiB of shared memory; 4096 streams are then
+// 2.8 waves of 1480 (with 9 warps they were 3.08 waves: a fourth, almost empty wave cost 25 %, sm__cycles_elapsed vs active)
+constexpr int RW_SPS = 1024, RW_N = 128, RW_WARPS = LB_RW_WARPS;
 
 #ifdef __CUDACC__
 struct RWWarp {
@@ -89,47 +97,53 @@ LB_D void rw_ifreq(const float2 *win, float *out, int w, int lane) {
 // volk_32f_x2_dot_prod_32f, :259-263), so the first maximum is the reference's sample index.
 //
 // Lane l owns the 32 consecutive lags 32 l + j.  At step k it needs f[32 l + k + j], j = 0..31: a window that slides by one
-// float per step, so it lives in registers (V, indexed modulo 64: two blocks of 32 steps, PAR = block parity, make every
-// register index a compile-time number) and ONE new float is loaded per step; the first version fetched all 32 from shared
+// float per step, so it lives in registers (V: 8 steps are unrolled so that every register index is a compile-time
+// number, then the window moves down by 8) and ONE new float is loaded per step; the first version fetched all 32 from shared
 // memory, 97 instructions per step and 22 % of the kernel's instructions.  Per step: 32 FMUL, 16 FADD2 (add.rn.f32x2 on
 // accumulator pairs), one LDS = 49 instructions.  The products stay scalar on purpose: ptxas contracts mul.rn.f32x2 +
 // add.rn.f32x2 into FFMA2 despite the explicit rounding (checked on the SASS, also with -fmad=false), which would round
 // once where the reference rounds twice; a scalar FMUL feeding a packed add is left alone.
 // f is read from the padded layout (33 floats per 32): the lanes are 33 floats apart, conflict-free.
-constexpr int RW_XC_LA = 8;                                           // a float is loaded this many steps before its first use
-LB_D int rw_xc_off(int n) { return n + (n >> 5); }                    // padded offset of float n of a lane's row sequence
-template <int PAR>
-LB_D void rw_xc_block(float (&V)[64], lb_u64 (&c2)[16], const float *rows, const float *u, bool short_block) {
+constexpr int RW_XC_B = 8;                                            // steps per unrolled block
+// one block of RW_XC_B steps; V[0 .. 31 + B) is the window on entry, moved down by B on exit.  The loop body is ~430
+// instructions: the fully unrolled form (32 steps, 27 KiB of code, no reuse) left 24 % of the stall samples in
+// "no instruction" -- nine warps streaming through different straight-line code defeat the instruction caches.
+LB_D void rw_xc_block(float (&V)[32 + RW_XC_B], lb_u64 (&c2)[16], const float *next, const float *u, int steps) {
 #ifdef __CUDA_ARCH__                                                  // (the packed helpers exist in the device pass only)
-    float4 uq = make_float4(0.f, 0.f, 0.f, 0.f);
+    float nv[RW_XC_B];
 #pragma unroll
-    for (int t = 0; t < 32; t++) {
-        if (t == 31 && short_block) continue;                         // k stops at sps - 2 (last step of the last block)
-        const int T = 32 * PAR + t;
-        // V[T + 32 + LA] (first used RW_XC_LA steps from now) replaces a float whose last use is long past
-        V[(T + 32 + RW_XC_LA) & 63] = rows[rw_xc_off(32 + RW_XC_LA + t)];
-        if ((t & 3) == 0) uq = *reinterpret_cast<const float4 *>(u + t);
-        const float ut = (t & 3) == 0 ? uq.x : (t & 3) == 1 ? uq.y : (t & 3) == 2 ? uq.z : uq.w;
+    for (int n = 0; n < RW_XC_B; n++) nv[n] = next[n];                // the floats the next block adds to the window
+    const float4 u0 = *reinterpret_cast<const float4 *>(u), u1 = *reinterpret_cast<const float4 *>(u + 4);
+    const float us[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-            c2[i] = add2(c2[i], pk2(__fmul_rn(V[(2 * i + T) & 63], ut), __fmul_rn(V[(2 * i + 1 + T) & 63], ut)));
+    for (int t = 0; t < RW_XC_B; t++) {
+        if (t < steps) {
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                c2[i] = add2(c2[i], pk2(__fmul_rn(V[2 * i + t], us[t]), __fmul_rn(V[2 * i + 1 + t], us[t])));
+        }
     }
+#pragma unroll
+    for (int n = 0; n < 32; n++) V[n] = V[n + RW_XC_B];
+#pragma unroll
+    for (int n = 0; n < RW_XC_B; n++) V[32 + n] = nv[n];
 #endif
 }
 // f: padded instantaneous frequency of two windows; up: up_ifreq (16-byte aligned).  Returns the warp's best key (0: no c > 0).
 LB_D unsigned long long rw_sync_xcorr(const float *f, const float *up, int lane) {
     unsigned long long best = 0ull;
 #ifdef __CUDA_ARCH__
-    float V[64];
+    float V[32 + RW_XC_B];
     lb_u64 c2[16];
 #pragma unroll
     for (int i = 0; i < 16; i++) c2[i] = pk2(0.0f, 0.0f);
-    const float *rows = f + 33 * lane;                                // float n of block m: rows[33 m + rw_xc_off(n)]
+    const float *rows = f + 33 * lane;                                // float n of this lane's sequence: rows[n + (n >> 5)]
 #pragma unroll
-    for (int n = 0; n < 64; n++) V[n] = n < 32 + RW_XC_LA ? rows[rw_xc_off(n)] : 0.0f;
-    for (int m2 = 0; m2 < RW_SPS / 64; m2++) {
-        rw_xc_block<0>(V, c2, rows + 33 * (2 * m2), up + 64 * m2, false);
-        rw_xc_block<1>(V, c2, rows + 33 * (2 * m2 + 1), up + 64 * m2 + 32, m2 == RW_SPS / 64 - 1);
+    for (int n = 0; n < 32 + RW_XC_B; n++) V[n] = rows[n + (n >> 5)];
+#pragma unroll 1
+    for (int b = 0; b < RW_SPS / RW_XC_B; b++) {
+        const int n0 = RW_XC_B * b + 32 + RW_XC_B;                    // first float of the next block's addition (8-aligned: one padded run)
+        rw_xc_block(V, c2, rows + n0 + (n0 >> 5), up + RW_XC_B * b, b == RW_SPS / RW_XC_B - 1 ? RW_XC_B - 1 : RW_XC_B);   // k stops at sps - 2
     }
 #pragma unroll
     for (int i = 0; i < 16; i++) {
@@ -173,22 +187,34 @@ LB_D int rw_fine_sync(const float *ifq, const float *up_v, int bin_idx, int sear
 // by one float per k, so it lives in registers (one new float per step) next to the 63 accumulators -- 65 instructions per
 // step.  The 32 partial sums of every lag are then added in lane order through a 32 x 63 scratch array.
 // ifq_p and up_vp are padded (float n at n + (n >> 5)): the lanes' rows are 33 floats apart, conflict-free.
-constexpr int RW_FS_LA = 6;
+constexpr int RW_FS_B = 4;                                            // products per unrolled block (see rw_xc_block on code size)
 LB_D int rw_fine_sync63(const float *ifq_p, const float *up_vp, float *scratch, int lane) {
     constexpr int first = RW_SPS - 31;                                // table index of (li = 0, k = 0); first % 32 == 1
     const float *a = ifq_p + 33 * lane;
     const float *w = up_vp + (first + (first >> 5)) + 33 * lane;      // W[n] = table[first + 32 lane + n] = w[n + ((n + 1) >> 5)]
-    float c[63], W[96];
+    float c[63], W[63 + RW_FS_B];
 #pragma unroll
     for (int li = 0; li < 63; li++) c[li] = 0.0f;
 #pragma unroll
-    for (int n = 0; n < 96; n++) W[n] = n < 62 + RW_FS_LA ? w[n + ((n + 1) >> 5)] : 0.0f;
+    for (int n = 0; n < 63 + RW_FS_B; n++) W[n] = w[n + ((n + 1) >> 5)];
+#pragma unroll 1
+    for (int b = 0; b < 32 / RW_FS_B; b++) {
+        float ak[RW_FS_B], nw[RW_FS_B];
+        const int n0 = RW_FS_B * (b + 1) + 63;                        // next block's additions: n0 .. n0 + B - 1 (n0 + 1 is 8-aligned)
 #pragma unroll
-    for (int kk = 0; kk < 32; kk++) {
-        if (kk + 62 + RW_FS_LA < 94) W[kk + 62 + RW_FS_LA] = w[kk + 62 + RW_FS_LA + ((kk + 63 + RW_FS_LA) >> 5)];
-        const float ak = a[kk];
+        for (int i = 0; i < RW_FS_B; i++) {
+            ak[i] = a[RW_FS_B * b + i];
+            const int n = n0 + i;
+            nw[i] = w[n + ((n + 1) >> 5)];                            // (read past the last needed float in the last block: inside the table)
+        }
 #pragma unroll
-        for (int li = 0; li < 63; li++) c[li] = fmaf(ak, W[kk + li], c[li]);
+        for (int i = 0; i < RW_FS_B; i++)
+#pragma unroll
+            for (int li = 0; li < 63; li++) c[li] = fmaf(ak[i], W[i + li], c[li]);
+#pragma unroll
+        for (int n = 0; n < 63; n++) W[n] = W[n + RW_FS_B];
+#pragma unroll
+        for (int i = 0; i < RW_FS_B; i++) W[63 + i] = nw[i];
     }
     __syncwarp();
 #pragma unroll

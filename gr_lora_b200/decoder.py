@@ -203,6 +203,11 @@ class decoder:
         N.check(self._L.lora_b200_last_cfo(self._h, int(stream), C.byref(cfo), C.byref(n)), "lora_b200_last_cfo")
         return float(cfo.value), int(n.value)
 
+    def reset(self):
+        """Every stream back to a freshly made block's state (a flowgraph restart); buffers and tables are kept."""
+        N.check(self._L.lora_b200_reset(self._h), "lora_b200_reset")
+        self.frames = []
+
     def state(self, stream=0):
         return N.check(self._L.lora_b200_stream_state(self._h, int(stream)), "lora_b200_stream_state")
 

@@ -83,6 +83,9 @@ typedef void (*lora_b200_frame_cb)(void *user, uint32_t stream, const uint8_t *f
 /* ---- lifecycle: decoder::make / ~decoder_impl (decoder_impl.cc:41-139) ---- */
 lora_b200_decoder *lora_b200_create(const lora_b200_config *cfg);
 void lora_b200_destroy(lora_b200_decoder *d);
+/* Every stream back to the state of a freshly made block (DETECT, empty power queue, no partial frame, counters 0): what
+ * stopping and restarting the flowgraph does to decoder_impl's members (:55-66).  Device buffers and tables are kept. */
+int lora_b200_reset(lora_b200_decoder *d);
 const char *lora_b200_last_error(void);
 int lora_b200_abi_version(void);
 

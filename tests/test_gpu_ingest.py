@@ -146,3 +146,22 @@ def test_frames_last_equals_callbacks(torch, oracle):
     fr2 = dec.frames_last()
     assert dec.frames == [] and fr2.tobytes() == fr.tobytes()
     dec.close()
+
+
+def test_reset_replays_identically(torch, oracle):
+    """lora_b200_reset: after it the same capture decodes to the same frames and consume amounts as on a new decoder, also
+    when the first pass stopped in the middle of a frame."""
+    import gr_lora_b200 as G
+    x, pays = _streams(7, 12, 2100)
+    n = x.shape[1]
+    dec = G.decoder(1e6, 125000, 7, False, 4, True, n_streams=12, quiet=True, max_items_per_call=n, max_frames_per_call=4)
+    c0 = dec.work_batch(x, callbacks=False).copy()
+    fr0 = dec.frames_last().tobytes()
+    dec.reset()
+    cut = (n * 2 // 3) // 1024 * 1024                    # stop inside a frame, then restart from scratch
+    dec.work_batch(np.ascontiguousarray(x[:, :cut]), callbacks=False)
+    dec.reset()
+    assert all(dec.state(s) == 0 for s in range(12))
+    c1 = dec.work_batch(x, callbacks=False).copy()
+    assert np.array_equal(c0, c1) and dec.frames_last().tobytes() == fr0 and len(fr0) > 0
+    dec.close()
