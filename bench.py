@@ -637,7 +637,11 @@ def run_e2e(args, torch, dist, G, device, local, world, rank, dec, iq, bins_ref,
         q = torch.view_as_real(dev_streams).mul(1.0 / scale).round_().clamp_(-32768, 32767).to(torch.int16)
         h_q = torch.empty((n_streams, n_items, 2), dtype=torch.int16, pin_memory=True)
         h_q.copy_(q)
-        del q, dev_streams
+        scale8 = 1.0 / 64.0
+        q8 = torch.view_as_real(dev_streams).mul(1.0 / scale8).round_().clamp_(-127, 127).to(torch.int8)
+        h_q8 = torch.empty((n_streams, n_items, 2), dtype=torch.int8, pin_memory=True)
+        h_q8.copy_(q8)
+        del q, q8, dev_streams
         torch.cuda.synchronize()
     except Exception as exc:     # e.g. not enough pinnable host memory on the box
         err = str(exc)[:200]
@@ -645,7 +649,7 @@ def run_e2e(args, torch, dist, G, device, local, world, rank, dec, iq, bins_ref,
     if all_min_int(1 if h_iq is not None else 0) != 1:
         return {"value": None, "unit": "symbols/s", "error": err or "pinned host allocation failed on another rank"}
 
-    def timed_rx(use_sc16):
+    def timed_rx(fmt):
         rx = G.decoder(1e6, 125000, sf, False, 4, False, n_streams=n_streams, demod="fft", device=local, quiet=True,
                        max_items_per_call=n_items, max_frames_per_call=frames_per_stream + 2)
         e_steps = max(3, min(args.steps, 5))
@@ -655,8 +659,10 @@ def run_e2e(args, torch, dist, G, device, local, world, rank, dec, iq, bins_ref,
             if world > 1:
                 dist.barrier()
             ta = time.perf_counter()
-            if use_sc16:
+            if fmt == "sc16":
                 consumed = rx.work_batch(h_q.data_ptr(), n_items=n_items, stride_items=n_items, host=1, sc16_scale=scale, callbacks=False)
+            elif fmt == "sc8":
+                consumed = rx.work_batch(h_q8.data_ptr(), n_items=n_items, stride_items=n_items, host=1, sc8_scale=scale8, callbacks=False)
             else:
                 consumed = rx.work_batch(h_iq.data_ptr(), n_items=n_items, stride_items=n_items, host=1, callbacks=False)
             fr = rx.frames_last()                          # the published frames, host side (inside the timed region)
@@ -675,9 +681,10 @@ def run_e2e(args, torch, dist, G, device, local, world, rank, dec, iq, bins_ref,
         return {"value": windows / dt, "s_per_step": dt, "frames_expected": int(all_sum(res[1])), "frames_ok": int(all_sum(res[2])),
                 "frames_published": int(all_sum(res[3])), "steps": e_steps}
 
-    cf = timed_rx(False)
-    sc = timed_rx(True)
-    del h_q
+    cf = timed_rx("cf32")
+    sc = timed_rx("sc16")
+    s8 = timed_rx("sc8")
+    del h_q, h_q8
     # the K1 batch entry point with host buffers (the K1 metric itself end to end)
     h_iq2 = h_iq.view(-1)[: n_sym_total * sps].view(n_sym_total, sps)
     h_iq2.copy_(iq)
@@ -708,6 +715,9 @@ def run_e2e(args, torch, dist, G, device, local, world, rank, dec, iq, bins_ref,
             "sc16": {"value": sc["value"], "unit": "symbols/s", "h2d_bytes_per_step": int(n_streams * n_items * 4),
                      "s_per_step": sc["s_per_step"], "frames_expected": sc["frames_expected"], "frames_ok": sc["frames_ok"],
                      "path": "lora_b200_work_batch_sc16 (int16 I/Q over PCIe, converted on the device)"},
+            "sc8": {"value": s8["value"], "unit": "symbols/s", "h2d_bytes_per_step": int(n_streams * n_items * 2),
+                    "s_per_step": s8["s_per_step"], "frames_expected": s8["frames_expected"], "frames_ok": s8["frames_ok"],
+                    "path": "lora_b200_work_batch_sc8 (int8 I/Q over PCIe, converted on the device)"},
             "k1_batch_host": k1h}
 
 

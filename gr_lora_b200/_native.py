@@ -57,6 +57,7 @@ SIGNATURES = {
     "lora_b200_work": (_i, [_vp, _u32, _vp, _sz, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_work_batch": (_i, [_vp, _vp, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_work_batch_sc16": (_i, [_vp, _vp, C.c_float, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
+    "lora_b200_work_batch_sc8": (_i, [_vp, _vp, C.c_float, _sz, _sz, _i, C.POINTER(_sz), FRAME_CB, _vp]),
     "lora_b200_frames_last": (_sz, [_vp, C.POINTER(_vp)]),
     "lora_b200_stream_state": (_i, [_vp, _u32]),
     "lora_b200_reset": (_i, [_vp]),

@@ -105,7 +105,8 @@ struct lora_b200_decoder {
     float2 *h_stage = nullptr;            // pinned, same shape
     size_t stage_cap = 0;                 // items
     std::vector<unsigned long long> h_consumed;
-    std::vector<RxFrameOut> h_frames, h_sorted;
+    RxFrameOut *h_frames = nullptr;           // pinned, frame_cap records
+    std::vector<RxFrameOut> h_sorted;
     std::vector<std::string> stdout_last;
     uint64_t launches = 0;
     bool cfo_estimate = false;            // lora_b200_set_cfo_estimate
@@ -380,14 +381,18 @@ int launch_rx(lora_b200_decoder *d, const RxParams &p, int grid, cudaStream_t st
 }
 
 void append_hex(std::string &s, const uint8_t *v, size_t n, bool endline, bool ascii) {   // print_vector_hex, utilities.h:351-368
-    char b[8];
-    std::string asc;
-    for (size_t i = 0; i < n; i++) {
-        snprintf(b, sizeof b, " %02x", v[i]);
-        s += b;
-        if (v[i] >= ' ' && v[i] <= '~') asc.push_back((char)v[i]);
+    static const char digits[] = "0123456789abcdef";
+    // (one snprintf per byte was 20 ms per call at 16 384 frames: more than the state machine of the last staging group)
+    const size_t at = s.size();
+    s.resize(at + 3 * n);
+    char *o = &s[at];
+    for (size_t i = 0; i < n; i++) { *o++ = ' '; *o++ = digits[v[i] >> 4]; *o++ = digits[v[i] & 15]; }
+    if (ascii) {
+        s += " (";
+        for (size_t i = 0; i < n; i++)
+            if (v[i] >= ' ' && v[i] <= '~') s.push_back((char)v[i]);
+        s += ")";
     }
-    if (ascii) s += " (" + asc + ")";
     if (endline) s += "\n";
 }
 
@@ -431,9 +436,9 @@ int rx_finish(lora_b200_decoder *d, uint32_t stream_base, uint32_t n_launch, siz
                        sizeof(unsigned long long) * n_launch, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (n_frames > d->frame_cap) n_frames = d->frame_cap;
-    d->h_frames.resize(n_frames);
     if (n_frames) {
-        CU(cudaMemcpyAsync(d->h_frames.data(), d->d_frames_out, sizeof(RxFrameOut) * n_frames, cudaMemcpyDeviceToHost, st));
+        if (!d->h_frames) CU(cudaMallocHost(&d->h_frames, sizeof(RxFrameOut) * d->frame_cap));      // pinned: the D2H runs at link speed
+        CU(cudaMemcpyAsync(d->h_frames, d->d_frames_out, sizeof(RxFrameOut) * n_frames, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
     }
     for (uint32_t s = 0; s < n_launch; s++) {
@@ -480,6 +485,24 @@ __global__ void sc16_to_cf32_kernel(const short2 *__restrict__ in, float2 *__res
             o[1] = make_float4(s2.x * scale, s2.y * scale, s3.x * scale, s3.y * scale);
         } else {
             for (size_t k = i; k < n && k < i + 4; k++) out[k] = make_float2(in[k].x * scale, in[k].y * scale);
+        }
+    }
+}
+
+// ... and interleaved int8 I/Q (GNU Radio's interleaved_char_to_complex; 2 bytes per sample over PCIe)
+__global__ void sc8_to_cf32_kernel(const char2 *__restrict__ in, float2 *__restrict__ out, size_t n, float scale) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 8;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < n; i += stride) {
+        if (i + 8 <= n && (((uintptr_t)(in + i)) & 15u) == 0 && (((uintptr_t)(out + i)) & 15u) == 0) {
+            const int4 v = __ldcs(reinterpret_cast<const int4 *>(in + i));
+            const int w[4] = {v.x, v.y, v.z, v.w};
+            float4 *o = reinterpret_cast<float4 *>(out + i);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                o[k] = make_float4((float)(signed char)(w[k] & 0xff) * scale, (float)(signed char)((w[k] >> 8) & 0xff) * scale,
+                                   (float)(signed char)((w[k] >> 16) & 0xff) * scale, (float)(signed char)((w[k] >> 24) & 0xff) * scale);
+        } else {
+            for (size_t k = i; k < n && k < i + 8; k++) out[k] = make_float2((float)in[k].x * scale, (float)in[k].y * scale);
         }
     }
 }
@@ -618,6 +641,7 @@ void lora_b200_destroy(lora_b200_decoder *d) {
     cudaFree(d->d_stage); cudaFree(d->d_stage16);
     for (cudaEvent_t e : d->stage_events) if (e) cudaEventDestroy(e);
     if (d->h_stage) cudaFreeHost(d->h_stage);
+    if (d->h_frames) cudaFreeHost(d->h_frames);
     delete d;
 }
 
@@ -839,7 +863,7 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
     const uint32_t ns = d->cfg.n_streams;
     for (uint32_t s = 0; s < ns; s++) consumed[s] = 0;
     if (n_items < 2 * (size_t)d->sps) return LORA_B200_OK;
-    const bool sc16 = elem == 4;
+    const bool sc16 = elem != sizeof(float2);             // an integer format (int16 or int8 I/Q) staged raw, converted on the device
     if (!host_ptr && !sc16) return run_rx(d, (const float2 *)iq, stride_items, n_items, 0, ns, consumed, cb, user);
     if (n_items > d->cfg.max_items_per_call) n_items = d->cfg.max_items_per_call;
     int rc = ensure_stage(d, n_items * ns, false, sc16);
@@ -872,7 +896,7 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
         const uint32_t s0 = g * gs, cnt = std::min<uint32_t>(gs, ns - s0);
         cudaStream_t xs = (g & 1) ? d->rx_stream2 : d->rx_stream;
         const uint8_t *src = (const uint8_t *)iq + (size_t)s0 * stride_items * elem;
-        void *dst = sc16 ? (void *)(d->d_stage16 + (size_t)s0 * n_items) : (void *)(d->d_stage + (size_t)s0 * n_items);
+        void *dst = sc16 ? (void *)((uint8_t *)d->d_stage16 + (size_t)s0 * n_items * elem) : (void *)(d->d_stage + (size_t)s0 * n_items);
         if (stride_items == n_items)                                  // dense rows: one linear copy (the 2-D form is for strided captures)
             CU(cudaMemcpyAsync(dst, src, elem * n_items * cnt, host_ptr ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, cs));
         else
@@ -883,7 +907,8 @@ static int work_batch_any(lora_b200_decoder *d, const void *iq, size_t elem, flo
         if (sc16) {
             const size_t n = (size_t)cnt * n_items;
             const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)d->n_sms * 8);
-            sc16_to_cf32_kernel<<<grid, 256, 0, xs>>>(d->d_stage16 + (size_t)s0 * n_items, d->d_stage + (size_t)s0 * n_items, n, scale);
+            if (elem == 4) sc16_to_cf32_kernel<<<grid, 256, 0, xs>>>(d->d_stage16 + (size_t)s0 * n_items, d->d_stage + (size_t)s0 * n_items, n, scale);
+            else sc8_to_cf32_kernel<<<grid, 256, 0, xs>>>((const char2 *)d->d_stage16 + (size_t)s0 * n_items, d->d_stage + (size_t)s0 * n_items, n, scale);
             d->launches++;
             CU(cudaGetLastError());
         }
@@ -915,6 +940,11 @@ int lora_b200_reset(lora_b200_decoder *d) {
     d->h_sorted.clear();
     for (auto &so : d->stdout_last) so.clear();
     return LORA_B200_OK;
+}
+
+int lora_b200_work_batch_sc8(lora_b200_decoder *d, const void *iq_sc8, float scale, size_t n_items, size_t stride_items,
+                             int host_ptr, size_t *consumed, lora_b200_frame_cb cb, void *user) {
+    return work_batch_any(d, iq_sc8, sizeof(char2), scale, n_items, stride_items, host_ptr, consumed, cb, user);
 }
 
 int lora_b200_stream_state(lora_b200_decoder *d, uint32_t stream) {

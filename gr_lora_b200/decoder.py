@@ -141,12 +141,12 @@ class decoder:
         buf = C.string_at(ptr.value, n * self.FRAME_DTYPE.itemsize)
         return np.frombuffer(buf, dtype=self.FRAME_DTYPE)
 
-    def work_batch(self, iq, n_items=None, stride_items=None, host=None, sc16_scale=None, callbacks=True):
-        """All streams at once. ``iq``: host ndarray [n_streams, n_items] (complex64, or int16 [n_streams, n_items, 2]
-        together with ``sc16_scale``) or a device tensor/pointer.  ``sc16_scale`` selects the int16 I/Q entry point:
-        the device computes x * scale, PCIe moves 4 bytes per sample."""
-        if isinstance(iq, np.ndarray) and sc16_scale is not None:
-            x = np.ascontiguousarray(iq, dtype=np.int16)
+    def work_batch(self, iq, n_items=None, stride_items=None, host=None, sc16_scale=None, callbacks=True, sc8_scale=None):
+        """All streams at once. ``iq``: host ndarray [n_streams, n_items] (complex64, or int16 / int8 [n_streams, n_items, 2]
+        together with ``sc16_scale`` / ``sc8_scale``) or a device tensor/pointer.  ``sc16_scale`` / ``sc8_scale`` select the
+        int16 / int8 I/Q entry points: the device computes x * scale, PCIe moves 4 / 2 bytes per sample."""
+        if isinstance(iq, np.ndarray) and (sc16_scale is not None or sc8_scale is not None):
+            x = np.ascontiguousarray(iq, dtype=np.int16 if sc16_scale is not None else np.int8)
             assert x.ndim == 3 and x.shape[0] == self.n_streams and x.shape[2] == 2
             ptr, n_items, stride_items, host = x.ctypes.data, x.shape[1], x.shape[1], 1
         elif isinstance(iq, np.ndarray):
@@ -164,6 +164,9 @@ class decoder:
         if sc16_scale is not None:
             N.check(self._L.lora_b200_work_batch_sc16(self._h, ptr, float(sc16_scale), int(n_items), int(stride_items), host,
                                                       cptr, cb, None), "lora_b200_work_batch_sc16")
+        elif sc8_scale is not None:
+            N.check(self._L.lora_b200_work_batch_sc8(self._h, ptr, float(sc8_scale), int(n_items), int(stride_items), host,
+                                                     cptr, cb, None), "lora_b200_work_batch_sc8")
         else:
             N.check(self._L.lora_b200_work_batch(self._h, ptr, int(n_items), int(stride_items), host, cptr, cb, None),
                     "lora_b200_work_batch")

@@ -161,6 +161,10 @@ int lora_b200_work_batch(lora_b200_decoder *d, const void *iq, size_t n_items, s
  * lora_b200_work_batch on the host-converted buffer. */
 int lora_b200_work_batch_sc16(lora_b200_decoder *d, const void *iq_sc16, float scale, size_t n_items, size_t stride_items,
                               int host_ptr, size_t *consumed /* [n_streams] */, lora_b200_frame_cb cb, void *user);
+/* ... and with int8 I/Q (interleaved signed bytes, GNU Radio's interleaved_char_to_complex followed by a multiply):
+ * a quarter of the gr_complex bytes over PCIe, the only lever left once the copy is the bound. */
+int lora_b200_work_batch_sc8(lora_b200_decoder *d, const void *iq_sc8, float scale, size_t n_items, size_t stride_items,
+                             int host_ptr, size_t *consumed /* [n_streams] */, lora_b200_frame_cb cb, void *user);
 /* Bulk access to what the last work / work_batch call published, for hosts that drain thousands of streams per call and do
  * not want one callback per frame (cb may be NULL then): records in delivery order (by stream, then by sequence), valid
  * until the next work call on this decoder.  `bytes` = loratap | loraphy | payload, `len` of them valid

@@ -165,3 +165,31 @@ def test_reset_replays_identically(torch, oracle):
     c1 = dec.work_batch(x, callbacks=False).copy()
     assert np.array_equal(c0, c1) and dec.frames_last().tobytes() == fr0 and len(fr0) > 0
     dec.close()
+
+
+def test_work_batch_sc8_equals_host_converted(torch, oracle):
+    """int8 I/Q: frames and consume amounts equal the oracle's on the host-converted buffer (x * scale in fp32), vector path
+    and the scalar tail of the converter."""
+    import gr_lora_b200 as G
+    sf, scale = 7, 1.0 / 64.0
+    x, pays = _streams(sf, 9, 4100)
+    q = np.stack([np.clip(np.round(x.real / scale), -127, 127), np.clip(np.round(x.imag / scale), -127, 127)], axis=-1).astype(np.int8)
+    back = (q[..., 0].astype(np.float32) * np.float32(scale) + 1j * (q[..., 1].astype(np.float32) * np.float32(scale))).astype(np.complex64)
+    n = x.shape[1]
+    dec = G.decoder(1e6, 125000, sf, False, 4, True, n_streams=9, quiet=True, max_items_per_call=n, max_frames_per_call=4)
+    consumed = dec.work_batch(q, sc8_scale=scale)
+    per = [[] for _ in range(9)]
+    for s, f in dec.frames:
+        per[s].append(f)
+    dec.close()
+    for k in range(9):
+        od = oracle.Decoder(sf=sf, cr=4, crc=True)
+        oc, _ = od.run(back[k])
+        assert int(consumed[k]) == oc and per[k] == od.frames(), k
+    assert sum(len(p) for p in per) >= 9
+    dec = G.decoder(1e6, 125000, sf, False, 4, True, n_streams=1, quiet=True, max_items_per_call=n, max_frames_per_call=4)
+    c1 = dec.work_batch(q[3:4, : n - 5], sc8_scale=scale)
+    od = oracle.Decoder(sf=sf, cr=4, crc=True)
+    oc, _ = od.run(back[3, : n - 5])
+    assert int(c1[0]) == oc and [f for _, f in dec.frames] == od.frames()
+    dec.close()
