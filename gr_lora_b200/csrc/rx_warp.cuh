@@ -49,8 +49,17 @@ struct RWSmem {
     RWWarp w[RW_WARPS];
 };
 
-// window samples [0, n) of the stream into the warp's buffer (8-byte accesses: the window starts at any sample)
-LB_D void rw_load(const float2 *__restrict__ g, float2 *win, int n, int lane) {
+// window samples [0, n) of the stream into the warp's buffer (8-byte accesses: the window starts at any sample); the lines
+// of the following window are requested into L2 meanwhile -- where the next step starts is only known at the end of this
+// one (consumed = sps +- fine sync), but it is within a few samples of g + n, and a step's first act is this load
+// (11 % of the stall samples sat on it, profiles/r2b_rx_warp.txt)
+LB_D void rw_load(const float2 *__restrict__ g, float2 *win, int n, int lane, const float2 *g_end) {
+    {
+        const char *nx = reinterpret_cast<const char *>(g + n) + 128 * lane;
+#pragma unroll
+        for (int j = 0; j < RW_SPS * 8 / (128 * 32); j++, nx += 128 * 32)
+            if (nx < reinterpret_cast<const char *>(g_end)) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx));
+    }
 #pragma unroll 8
     for (int k = lane; k < n; k += 32) win[k] = __ldcs(g + k);
 }
@@ -325,7 +334,7 @@ rx_warp_kernel(RxParams p) {
             break;
         }
         case LORA_B200_FIND_SFD: {                                // :785-818, A10
-            rw_load(x, win, sps, lane);
+            rw_load(x, win, sps, lane, xs + p.n_items);
             __syncwarp();
             rw_ifreq<true>(win, ifq, sps, lane);                  // padded: float i at i + (i >> 5) = lane + 33 j for i = lane + 32 j
             const int to_idx = sps - 1;
@@ -367,7 +376,7 @@ rx_warp_kernel(RxParams p) {
         case LORA_B200_DECODE_HEADER:
         case LORA_B200_DECODE_PAYLOAD: {                          // :826-886
             const bool is_first = state == LORA_B200_DECODE_HEADER;
-            rw_load(x, win, sps, lane);
+            rw_load(x, win, sps, lane, xs + p.n_items);
             __syncwarp();
             bool do_demod = true;
             if (!is_first && p.implicit) {                        // :861 determine_energy
