@@ -47,7 +47,7 @@ LB_D float2 cmul_const(float2 a, float wx, float wy) {
 // lib/decoder_impl.cc:436-438):  a*b = (b.x, b.y)*a.x + (-b.y, b.x)*a.y
 // Operand ORDER matters: with the swapped / half-negated pair as the FIRST multiplicand ptxas folds the swap and the sign
 // into operand modifiers (FMUL2 R, -Rb.F32x2.LO_HI.NP, Ra.F32), so a complex product is exactly two instructions; with
-// the broadcast first it materialises the pair with a MOV and an FADD (measured on the SASS, profiles/r2_cmul_sass.md).
+// the broadcast first it materialises the pair with a MOV and an FADD (measured on the SASS; A/B per kernel in profiles/r2_packed_cmul_ab.jsonl).
 LB_D float2 cmul(float2 a, float2 b) {
     return up2(fma2(pk2(b.x, b.y), pk2(a.x, a.x), mul2(pk2(-b.y, b.x), pk2(a.y, a.y))));
 }

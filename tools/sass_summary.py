@@ -10,10 +10,10 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-FAMILIES = ["UBLKCP", "UTMALDG", "SYNCS", "LDTM", "STTM", "FFMA2", "FADD2", "FMUL2", "FFMA", "LDS", "STS", "LDG", "SHFL", "BAR", "MEMBAR", "UTCALLOC", "UTCMMA", "HMMA"]
+FAMILIES = ["UBLKCP", "UTMALDG", "SYNCS", "STAS", "LDTM", "STTM", "CREDUX", "FFMA2", "FADD2", "FMUL2", "FFMA", "LDS", "STS", "LDG", "SHFL", "BAR", "MEMBAR", "UTCALLOC", "UTCMMA", "HMMA"]
 DEFAULT = ["k1_sf7_warp_kernelILi12ELi2E", "k1_group_kernelILi8ELi6ELi2E", "k1_group_kernelILi9ELi3ELi2E", "k1_sf10_kernelILi3E",
-           "k1_rows_kernelILi11E", "k1_rows_kernelILi12E", "rx_stream_kernelILi7ELb0E", "rx_stream_kernelILi7ELb1E", "k8_frames_kernel",
-           "chan_fir_kernel", "sc16_to_cf32_kernel", "k1_finalize_kernel"]
+           "k1_rows_kernelILi11E", "k1_rows_kernelILi12E", "rx_warp_kernelILb1E", "rx_warp_kernelILb0E", "rx_stream_kernelILi8ELb1E", "k8_frames_kernel",
+           "chan_fir_kernel", "sc16_to_cf32_kernel", "sc8_to_cf32_kernel", "k1_finalize_kernel"]
 
 
 def main():
@@ -28,7 +28,7 @@ def main():
             cur = m.group(1)
             kernels[cur] = collections.Counter()
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(.*?);", ln)
+        m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(.*?);", ln)
         if m and cur:
             toks = m.group(1).split()
             op = toks[1] if toks[0].startswith("@") and len(toks) > 1 else toks[0]
@@ -56,7 +56,7 @@ def main():
     print()
     print("Whole library: " + ", ".join(f"{k} {tot.get(k, 0)}" for k in FAMILIES) + f"; instructions {tot['_total']}.")
     print("UTCMMA / HMMA = 0: no tensor-core matrix product (the north star asks for none); UBLKCP / UTMALDG = TMA bulk and "
-          "tensor-map copies, SYNCS = mbarrier, LDTM / STTM = tcgen05.ld / tcgen05.st and UTCALLOC = tcgen05.alloc / dealloc (the dechirp table and twiddles of "
+          "tensor-map copies, SYNCS = mbarrier, STAS = st.async into the peer CTA (SF12 exchange), CREDUX = the warp argmax (redux.sync), LDTM / STTM = tcgen05.ld / tcgen05.st and UTCALLOC = tcgen05.alloc / dealloc (the dechirp table and twiddles of "
           "k1_rows live in tensor memory), FFMA2 / FADD2 / FMUL2 = packed fp32.")
 
 
