@@ -472,6 +472,14 @@ int run_rx(lora_b200_decoder *d, const float2 *d_iq, size_t stride_items, size_t
     return rc;
 }
 
+// A3 on a batch of windows: one warp per window, the stream kernel's rw_ifreq on global memory
+__global__ void k3_ifreq_kernel(const float2 *__restrict__ iq, size_t n_windows, uint32_t window, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const size_t warps = (size_t)gridDim.x * (blockDim.x >> 5);
+    for (size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_windows; w += warps)
+        rw_ifreq<false>(iq + w * window, out + w * window, (int)window, lane);
+}
+
 // SDR-native ingest: interleaved int16 I/Q -> gr_complex scaled by `scale` (what a host-side sc16 -> fc32 converter does)
 __global__ void sc16_to_cf32_kernel(const short2 *__restrict__ in, float2 *__restrict__ out, size_t n, float scale) {
     const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
@@ -792,6 +800,18 @@ int lora_b200_demod_gradient_dev(lora_b200_decoder *d, const void *iq, size_t n_
     const int grid = (int)std::min<size_t>(n_symbols, (size_t)d->k2_grid);
     k2_gradient_kernel<<<grid, RX_THREADS, 0, (cudaStream_t)stream>>>((const float2 *)iq, n_symbols, d->sps, d->n_bins, d->decim,
                                                                      d->d_k2_scratch, bins);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+int lora_b200_ifreq_dev(lora_b200_decoder *d, const void *iq, size_t n_windows, uint32_t window, float *out, void *stream) {
+    if (!d || (!iq && n_windows) || (!out && n_windows)) return fail(LORA_B200_EINVAL, "null argument");
+    if (window == 0 || window % 128u) return fail(LORA_B200_EINVAL, "window must be a positive multiple of 128");
+    CU(cudaSetDevice(d->device));
+    if (n_windows == 0) return LORA_B200_OK;
+    const int grid = (int)std::min<size_t>((n_windows + 7) / 8, (size_t)d->n_sms * 8);
+    k3_ifreq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2 *)iq, n_windows, window, out);
     d->launches++;
     CU(cudaGetLastError());
     return LORA_B200_OK;

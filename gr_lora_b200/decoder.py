@@ -258,6 +258,11 @@ class decoder:
         N.check(self._L.lora_b200_demod_fft_host_sc16(self._h, ptr, float(scale), n, bp, mp), "lora_b200_demod_fft_host_sc16")
         return bins, mags
 
+    def ifreq(self, iq_dev, n_windows, window, out_dev, cuda_stream=0):
+        """A3 instantaneous_frequency of n_windows windows of `window` samples (device tensors)."""
+        N.check(self._L.lora_b200_ifreq_dev(self._h, _dev_ptr(iq_dev), int(n_windows), int(window), _dev_ptr(out_dev),
+                                           int(cuda_stream)), "lora_b200_ifreq_dev")
+
     def demod_gradient(self, iq_dev, n_symbols, bins_dev, cuda_stream=0):
         N.check(self._L.lora_b200_demod_gradient_dev(self._h, _dev_ptr(iq_dev), int(n_symbols), _dev_ptr(bins_dev),
                                                     int(cuda_stream)), "lora_b200_demod_gradient_dev")

@@ -132,6 +132,10 @@ int lora_b200_demod_fft_host_sc16(lora_b200_decoder *d, const void *iq_sc16, flo
 /* K2: max_frequency_gradient_idx on aligned windows (:466-491), same layout */
 int lora_b200_demod_gradient_dev(lora_b200_decoder *d, const void *iq, size_t n_symbols,
                                  uint32_t *bins, void *cuda_stream);
+/* A3: instantaneous_frequency (:224-244) of n_windows windows of `window` gr_complex each (window a multiple of 128),
+ * out[n_windows][window] floats; the last value of a window repeats the one before it (:243).  The arg() per sample is
+ * the stream kernels' own (1.8 ulp; the values agree with libm-based ones to 1e-6 rad); device pointers, async on cuda_stream. */
+int lora_b200_ifreq_dev(lora_b200_decoder *d, const void *iq, size_t n_windows, uint32_t window, float *out, void *cuda_stream);
 
 /* ---- K8: integer decode of whole code-word vectors (decode(), :567-586, B2-B4) ----
  * For each of n_vec vectors: codewords[i*stride .. +lengths[i]) -> deshuffle, dewhiten,
