@@ -10,9 +10,10 @@
 //     branches (8 x 2048 points = 128 KiB).  SF12: a cluster of two CTAs per symbol, CTA c takes branches 4c .. 4c+3 (4 x 4096
 //     points = 128 KiB, the 32-byte halves of every 64-byte group of samples, fetched with a 2-D tensor-map TMA so that L2
 //     delivers every sector once); the only data that crosses SMs is one partial sum per output bin (16 KiB per symbol
-//     and direction, DSMEM) -- 1/16 of the symbol.
+//     and direction, st.async into the peer's shared memory) -- 1/16 of the symbol; the receiving warp parks its own
+//     half in tensor memory and completes the sums one symbol later.
 //   * a symbol is 16 ROWS of 8 KiB (row j = n1 in [j L/16, (j+1) L/16), all local branches).  Rows live in a pool of
-//     28 (26) shared-memory slots of 8 KiB that rotates: global row g of this CTA's symbol sequence sits in slot g mod P.
+//     28 (SF12: 24) shared-memory slots of 8 KiB that rotates: global row g of this CTA's symbol sequence sits in slot g mod P.
 //     16 slots hold the symbol being transformed, the others receive the next rows by TMA while it is; a slot is
 //     re-armed by the warp that finished with it.  All three FFT passes are IN PLACE, so shared-memory traffic is
 //     6 x 8 B per sample (TMA write, three read-modify passes): 48 B against the 128 B/clk crossbar = 0.8 of the HBM

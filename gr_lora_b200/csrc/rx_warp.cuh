@@ -17,9 +17,10 @@
 //     sample on ties).  The 63-lag fine_sync of the preamble uses the same register-resident window per
 //     lane over a block of 32 products; the three-lag fine_sync of a payload symbol keeps the CTA kernel's lane-strided
 //     order.  arg() is lb_atan2f (lora_common.cuh), four groups of 32 samples at a time.
-//   * what bounds it: two warps per scheduler, every one a chain of dependent steps (ncu, profiles/r2_rx_sf7_warp.txt:
-//     issue slots 35 % active, stall "wait" 38 %); the listed changes took 4096 streams x 256 windows from 2.24e7 to
-//     2.64e7 windows/s.
+//   * what bounds it: two or three warps per scheduler, every one a chain of dependent steps (ncu,
+//     profiles/r2_rx_warp_final.txt: issue slots 42 % active, stalls wait 24 %, long scoreboard 18 %); 4 700 warp
+//     instructions per window, a third of them the per-sample arg() and unwrap.  The kernel alone runs 4096 streams x 256
+//     windows in 12 ms (8.7e7 windows/s); history in profiles/r2_rx_path.md.
 // Same observable behaviour as rx_stream_kernel: frames, consume amounts, per-step trace.  Other SFs and sample rates use
 // rx_stream_kernel.
 #pragma once
