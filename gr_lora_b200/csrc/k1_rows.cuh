@@ -419,6 +419,8 @@ k1_rows_kernel(const __grid_constant__ RParams P) {
             tm_ld16(tm_lane + (uint32_t)(R_TM_TW0 + 32 * (warp >> 2) + 16), tw + 8);
             tm_wait_ld();
             r_twiddle16(v0, v1, tw);
+            __syncwarp();      // the loads read the TMA's linear layout, the stores write the swizzled one: inside the warp's own
+                               // block, but lanes swap units -- every lane's loads before any lane's stores
 #pragma unroll
             for (int kc = 0; kc < 16; kc++) {
                 const int br = bitrev<16>(kc);

@@ -491,6 +491,7 @@ rx_warp_kernel(RxParams p) {
                     }
                 }
             }
+            __syncwarp();                                         // lane 0's stores to the decoder state above -> every lane's reads below
             flag = __shfl_sync(0xffffffffu, flag, 0);
             frame_slot = __shfl_sync(0xffffffffu, frame_slot, 0);
             if (flag == 2) next_state = LORA_B200_DECODE_PAYLOAD;
