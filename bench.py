@@ -288,8 +288,22 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # synthetic inputs
 # ---------------------------------------------------------------------------------------------------------------------
+_TX_DECODERS = {}
+
+
+def _tx_decoder(torch, sf, device):
+    """A decoder handle for the library's device-side transmitter / channel kernels (lora_b200_tx_*), one per (SF, GPU)."""
+    import gr_lora_b200 as G
+    idx = device.index if getattr(device, "index", None) is not None else torch.cuda.current_device()
+    key = (sf, idx)
+    if key not in _TX_DECODERS:
+        _TX_DECODERS[key] = G.decoder(1e6, 125000, sf, False, 4, False, sf > 10, False, n_streams=1, device=idx, quiet=True)
+    return _TX_DECODERS[key]
+
+
 def synth_batch(torch, sf, n_sym, snr_db, device, seed, out=None, cfo_hz_per_symbol=None):
-    """[n_sym, sps] cf32 on the device: chirp shift = value, unit amplitude, AWGN; optional per-symbol CFO (Hz)."""
+    """[n_sym, sps] cf32 on the device: chirp shift = value, unit amplitude, AWGN; optional per-symbol CFO (Hz).
+    Generated by the library's tx_symbols kernel (csrc/tx_channel.cuh) from the host modulator's chirp table."""
     from gr_lora_b200 import tx
     n_bins, sps = 1 << sf, 8 << sf
     up = torch.from_numpy(tx.base_upchirp(sf).astype(np.complex64)).to(device)
@@ -299,18 +313,9 @@ def synth_batch(torch, sf, n_sym, snr_db, device, seed, out=None, cfo_hz_per_sym
     iq = out if out is not None else torch.empty((n_sym, sps), dtype=torch.complex64, device=device)
     iq = iq.view(-1)[: n_sym * sps].view(n_sym, sps)
     sigma = float(np.sqrt(10.0 ** (-snr_db / 10.0) / 2.0))
-    ar = torch.arange(sps, device=device, dtype=torch.int64)
-    chunk = max(1, (256 << 20) // (8 * sps))
-    iqr = torch.view_as_real(iq)
-    for s in range(0, n_sym, chunk):
-        e = min(n_sym, s + chunk)
-        idx = (ar[None, :] + vals[s:e, None] * 8) % sps
-        blk = up[idx]
-        if cfo_hz_per_symbol is not None:
-            ph = (2.0 * math.pi / 1e6) * cfo_hz_per_symbol[s:e, None].to(torch.float64) * ar[None, :].to(torch.float64)
-            blk = blk * torch.polar(torch.ones_like(ph, dtype=torch.float32), ph.remainder(2.0 * math.pi).to(torch.float32))
-        iq[s:e] = blk
-        iqr[s:e].add_(torch.randn((e - s, sps, 2), generator=gen, device=device, dtype=torch.float32), alpha=sigma)
+    cfo = None if cfo_hz_per_symbol is None else cfo_hz_per_symbol.to(device=device, dtype=torch.float32).contiguous()
+    _tx_decoder(torch, sf, device).tx_symbols(vals.to(torch.int32), iq, n_sym, noise_sigma=sigma, seed=seed, cfo_hz_dev=cfo, up_table_dev=up)
+    torch.cuda.synchronize(device)
     return iq, vals
 
 
@@ -339,21 +344,14 @@ def frame_stream(sf, n_items, seed, payload_len=12, snr_db=None, lead=None):
 
 
 def expand_streams(torch, base_caps, n_streams, snr_db, device, seed):
-    """[n_streams, n_items] on the device: stream s = base capture s mod K + its own AWGN."""
+    """[n_streams, n_items] on the device: stream s = base capture s mod K + its own AWGN (the library's tx_expand kernel)."""
     k = len(base_caps)
     n_items = base_caps[0].size
     base = torch.from_numpy(np.stack(base_caps)).to(device)
     out = torch.empty((n_streams, n_items), dtype=torch.complex64, device=device)
-    gen = torch.Generator(device=device)
-    gen.manual_seed(seed)
     sigma = float(np.sqrt(10.0 ** (-snr_db / 10.0) / 2.0))
-    step = max(k, (256 << 20) // (8 * n_items) // k * k)
-    outr = torch.view_as_real(out)
-    for s in range(0, n_streams, step):
-        e = min(n_streams, s + step)
-        idx = torch.arange(s, e, device=device) % k
-        out[s:e] = base[idx]
-        outr[s:e].add_(torch.randn((e - s, n_items, 2), generator=gen, device=device, dtype=torch.float32), alpha=sigma)
+    _tx_decoder(torch, 7, device).tx_expand(base, k, n_items, n_streams, out, noise_sigma=sigma, seed=seed)
+    torch.cuda.synchronize(device)
     return out
 
 

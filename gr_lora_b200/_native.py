@@ -53,6 +53,8 @@ SIGNATURES = {
     "lora_b200_demod_fft_host_sc16": (_i, [_vp, _vp, C.c_float, _sz, _vp, _vp]),
     "lora_b200_demod_gradient_dev": (_i, [_vp, _vp, _sz, _vp, _vp]),
     "lora_b200_ifreq_dev": (_i, [_vp, _vp, _sz, _u32, _vp, _vp]),
+    "lora_b200_tx_symbols_dev": (_i, [_vp, _vp, _vp, _vp, C.c_float, C.c_uint64, _sz, _vp, _vp]),
+    "lora_b200_tx_expand_dev": (_i, [_vp, _vp, _u32, _sz, C.c_float, C.c_uint64, _sz, _vp, _vp]),
     "lora_b200_decode_codewords_dev": (_i, [_vp, _vp, _vp, _sz, _vp, _vp, _sz, _vp, _sz, _vp, _vp]),
     "lora_b200_deinterleave_dev": (_i, [_vp, _vp, _u32, _u32, _sz, _vp, _vp]),
     "lora_b200_work": (_i, [_vp, _u32, _vp, _sz, C.POINTER(_sz), FRAME_CB, _vp]),

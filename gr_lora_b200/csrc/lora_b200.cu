@@ -9,6 +9,7 @@
 #include "k1_sf10.cuh"
 #include "rx_stream.cuh"
 #include "rx_warp.cuh"
+#include "tx_channel.cuh"
 #include "k1_rows.h"
 #include "k1_packed.h"
 
@@ -959,6 +960,37 @@ int lora_b200_reset(lora_b200_decoder *d) {
     if (d->d_trace_n) CU(cudaMemset(d->d_trace_n, 0, sizeof(uint32_t) * d->cfg.n_streams));
     d->h_sorted.clear();
     for (auto &so : d->stdout_last) so.clear();
+    return LORA_B200_OK;
+}
+
+int lora_b200_tx_symbols_dev(lora_b200_decoder *d, const void *up_table, const uint32_t *values, const float *cfo_hz, float noise_sigma,
+                             uint64_t seed, size_t n_symbols, void *out, void *stream) {
+    if (!d || (!values && n_symbols) || (!out && n_symbols)) return fail(LORA_B200_EINVAL, "null argument");
+    if (d->sps & 1u) return fail(LORA_B200_EUNSUPPORTED, "odd samples per symbol");
+    CU(cudaSetDevice(d->device));
+    if (n_symbols == 0) return LORA_B200_OK;
+    const float2 *up = up_table ? (const float2 *)up_table : tab<float2>(d, d->toff.up);
+    const size_t threads = n_symbols * (d->sps / 2);
+    const int grid = (int)std::min<size_t>((threads + 255) / 256, (size_t)d->n_sms * 16);
+    tx_symbols_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(up, d->sps, d->decim, values, cfo_hz, 1.0 / (double)d->cfg.samp_rate, noise_sigma,
+                                                              (unsigned long long)seed, n_symbols, (float2 *)out);
+    d->launches++;
+    CU(cudaGetLastError());
+    return LORA_B200_OK;
+}
+
+int lora_b200_tx_expand_dev(lora_b200_decoder *d, const void *base, uint32_t k, size_t n_items, float noise_sigma, uint64_t seed,
+                            size_t n_streams, void *out, void *stream) {
+    if (!d || !base || !out || k == 0) return fail(LORA_B200_EINVAL, "null argument");
+    if (n_items & 1u) return fail(LORA_B200_EINVAL, "n_items must be even");
+    CU(cudaSetDevice(d->device));
+    if (n_streams == 0 || n_items == 0) return LORA_B200_OK;
+    const size_t threads = n_streams * (n_items / 2);
+    const int grid = (int)std::min<size_t>((threads + 255) / 256, (size_t)d->n_sms * 16);
+    tx_expand_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2 *)base, k, n_items, noise_sigma, (unsigned long long)seed, n_streams,
+                                                             (float2 *)out);
+    d->launches++;
+    CU(cudaGetLastError());
     return LORA_B200_OK;
 }
 

@@ -258,6 +258,16 @@ class decoder:
         N.check(self._L.lora_b200_demod_fft_host_sc16(self._h, ptr, float(scale), n, bp, mp), "lora_b200_demod_fft_host_sc16")
         return bins, mags
 
+    def tx_symbols(self, values_dev, out_dev, n_symbols, noise_sigma=0.0, seed=0, cfo_hz_dev=None, up_table_dev=None, cuda_stream=0):
+        """Synthetic aligned data symbols on the device (chirp shift = value, optional per-symbol CFO and AWGN)."""
+        N.check(self._L.lora_b200_tx_symbols_dev(self._h, _dev_ptr(up_table_dev), _dev_ptr(values_dev), _dev_ptr(cfo_hz_dev), float(noise_sigma), int(seed),
+                                                int(n_symbols), _dev_ptr(out_dev), int(cuda_stream)), "lora_b200_tx_symbols_dev")
+
+    def tx_expand(self, base_dev, k, n_items, n_streams, out_dev, noise_sigma=0.0, seed=0, cuda_stream=0):
+        """n_streams channels from k base captures plus every stream's own AWGN, on the device."""
+        N.check(self._L.lora_b200_tx_expand_dev(self._h, _dev_ptr(base_dev), int(k), int(n_items), float(noise_sigma), int(seed),
+                                               int(n_streams), _dev_ptr(out_dev), int(cuda_stream)), "lora_b200_tx_expand_dev")
+
     def ifreq(self, iq_dev, n_windows, window, out_dev, cuda_stream=0):
         """A3 instantaneous_frequency of n_windows windows of `window` samples (device tensors)."""
         N.check(self._L.lora_b200_ifreq_dev(self._h, _dev_ptr(iq_dev), int(n_windows), int(window), _dev_ptr(out_dev),

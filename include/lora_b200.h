@@ -137,6 +137,18 @@ int lora_b200_demod_gradient_dev(lora_b200_decoder *d, const void *iq, size_t n_
  * the stream kernels' own (1.8 ulp; the values agree with libm-based ones to 1e-6 rad); device pointers, async on cuda_stream. */
 int lora_b200_ifreq_dev(lora_b200_decoder *d, const void *iq, size_t n_windows, uint32_t window, float *out, void *cuda_stream);
 
+/* ---- synthetic transmitter / channel on the device (the reference is a receiver only) ----
+ * tx_symbols: n_symbols aligned data symbols, out[s][n] = up[(n + decim * values[s]) mod sps] * e^{j 2 pi cfo_hz[s] n / fs}
+ *   + noise_sigma * (N(0,1) + j N(0,1)).  up_table = device cf32[sps] or NULL for the decoder's own ideal up-chirp
+ *   (lib/decoder_impl.cc:149-160: (1 + 1j) e^{j phase}, i.e. amplitude sqrt 2); cfo_hz = device float[n_symbols] or NULL; noise_sigma = 0: no noise.  The noise is a
+ *   counter-based generator (Philox4x32-10) keyed by `seed`: the same call gives the same samples on any launch geometry.
+ * tx_expand: n_streams concurrent channels from k base captures, out[s] = base[s mod k] + the stream's own noise
+ *   (base device cf32[k][n_items], n_items even).  Device pointers, async on cuda_stream. */
+int lora_b200_tx_symbols_dev(lora_b200_decoder *d, const void *up_table, const uint32_t *values, const float *cfo_hz,
+                             float noise_sigma, uint64_t seed, size_t n_symbols, void *out, void *cuda_stream);
+int lora_b200_tx_expand_dev(lora_b200_decoder *d, const void *base, uint32_t k, size_t n_items, float noise_sigma, uint64_t seed,
+                            size_t n_streams, void *out, void *cuda_stream);
+
 /* ---- K8: integer decode of whole code-word vectors (decode(), :567-586, B2-B4) ----
  * For each of n_vec vectors: codewords[i*stride .. +lengths[i]) -> deshuffle, dewhiten,
  * Hamming decode.  out[i*out_stride ..]; out_len[i] = bytes produced.  cr[i] = d_phdr.cr,
