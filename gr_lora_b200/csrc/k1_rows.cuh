@@ -88,7 +88,6 @@ template <int SF> LB_HD int r_sample(int rank, int warp, int lane, int j) {
 // lanes of every quarter met in one bank group, ncu: 2x the ideal wavefronts on the pass-2 loads.)
 template <int SF> LB_HD int r_swz(int block) { return SF == 11 ? ((block & 1) | ((block & 2) << 1)) : ((block & 3) << 1); }
 template <int SF> LB_HD int r_unit(int block, int within) { return block * 32 + (within ^ r_swz<SF>(block)); }   // float4 index in a row
-template <int SF> LB_HD int r_signed_bin(int k) { return k < RCfg<SF>::L / 2 ? k : k - RCfg<SF>::L; }
 // exponent (mod sps) of the per-q2 factor of W_sps^{e k'}: k' = kc + 16 kb + 256 q2 - (q2 >= A0/2 ? L : 0)
 template <int SF> LB_HD int r_cq_exp(int e, int q2) {
     using C = RCfg<SF>;
@@ -170,15 +169,6 @@ LB_D uint32_t map_to_peer(uint32_t local_smem_addr, uint32_t peer) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(peer));
     return r;
 }
-LB_D void st_peer_f4(uint32_t peer_addr, float4 v) {
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(peer_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-}
-LB_D void st_peer_f2(uint32_t peer_addr, float2 v) {
-    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(peer_addr), "f"(v.x), "f"(v.y) : "memory");
-}
-LB_D void mbar_arrive_peer(uint32_t peer_bar_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar_addr) : "memory");
-}
 LB_D void mbar_arrive_peer_relaxed(uint32_t peer_bar_addr) {
     asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(peer_bar_addr) : "memory");
 }
@@ -187,14 +177,6 @@ LB_D void st_async_peer_f4(uint32_t peer_dst, float4 v, uint32_t peer_bar) {
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
                  ::"r"(peer_dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(peer_bar) : "memory");
 }
-LB_D void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {      // acquire at cluster scope: the peer's DSMEM stores are visible after it
-    uint32_t ok;
-    do {
-        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-LB_D void fence_cluster() { asm volatile("fence.acq_rel.cluster;" ::: "memory"); }
 LB_D void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
