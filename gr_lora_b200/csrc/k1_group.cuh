@@ -14,7 +14,8 @@
 // multiplies with are symbol-invariant and live in tensor memory (tmem.cuh; 64 columns per thread, 12 warps = 3 per lane
 // quadrant = 192 columns), like k1_sf10's: the shared-memory chirp table of round 1 was a sixth of the traffic of a kernel
 // whose L1 / shared pipe was the busiest unit (ncu profiles/r2_k1_sf9.txt: l1tex 68 %).  -DLB_GROUP_CHIRP_SMEM builds the
-// old form for A/B runs.
+// old form for A/B runs.  (The 16 KiB this frees at SF8 hold a seventh group, but 14 warps leave 128 registers per thread:
+// measured 0.775 against 0.881 with six groups, profiles/r2_group_chirp_tmem_ab.jsonl.)
 #pragma once
 #include "k1_warp.cuh"
 #include "tmem.cuh"
