@@ -3,7 +3,8 @@
 
 Headline workload (BASELINE.json configs[1]): batched synthetic SF7 BW125k at 1 MS/s,
 4096 concurrent channels x 256 aligned symbols per channel = 1 048 576 symbols = 8 GiB of cf32 per GPU per step,
-symbol values ~ U[0,128), AWGN +10 dB, generated on the device.  A "step" = one pass of K1 over the whole batch.  The
+symbol values ~ U[0,128), AWGN +10 dB, generated on the device by the library's own transmitter kernels
+(lora_b200_tx_symbols_dev / lora_b200_tx_expand_dev).  A "step" = one pass of K1 over the whole batch.  The
 input (8 GiB) is far larger than the 126 MB L2, so no L2 flush is needed between timed iterations.
 
 One JSON line:
@@ -15,14 +16,15 @@ One JSON line:
   e2e           the reference-facing call with HOST buffers: frame-bearing SF7 streams (4096 channels x 256 symbol
                 times, pinned) -> lora_b200_work_batch (H2D, detect / sync / demodulate with the FFT demodulator /
                 decode, frames D2H) -> every expected frame checked; value = symbol windows consumed per second.
-                Sub-keys: sc16 (the same through lora_b200_work_batch_sc16, int16 I/Q over PCIe) and k1_batch_host
+                Sub-keys: sc16 / sc8 (the same through lora_b200_work_batch_sc16 / _sc8, int16 / int8 I/Q over PCIe) and k1_batch_host
                 (lora_b200_demod_fft_host on the headline batch: the K1 metric itself through host buffers)
   config4       BASELINE.json configs[3]: 64 channels x SF7..SF12 = 384 streams x 2 s, dealt stream_id mod N over
                 the ranks, host buffers -> work_batch -> frames, every expected frame checked
   cpu_baseline  the reference's own get_shift_fft (oracle/_ref: lib/decoder_impl.cc compiled against stand-in
                 headers; kind "reference") or, where that build is absent, the C restatement (kind "port"), on the
                 host cores, bounded sample; plus the reference's work() on frame-bearing streams
-  --impl reference   times only that CPU path (all host threads it may use) and prints the same JSON shape
+  --impl reference   times only that CPU path (all host threads it may use) and prints the same JSON shape; work_path
+                adds the reference's own work() rate, the like-for-like figure for the GPU arm's e2e
 
 Multi-GPU (torchrun): streams are independent, every rank owns its own batch (weak scaling, no per-symbol
 collective); the chirp / twiddle tables are broadcast once from rank 0 with NCCL at init.  Each rank
