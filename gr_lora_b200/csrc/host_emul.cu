@@ -52,6 +52,11 @@ int lb_k1_emulate_rows(int sf, const float2 *x, size_t n_symbols, const float2 *
 }
 
 
+// the stream kernels' arg() (lora_common.cuh), on the host
+void lb_emul_atan2f(const float *y, const float *x, float *out, size_t n) {
+    for (size_t i = 0; i < n; i++) out[i] = lb::lb_atan2f(y[i], x[i]);
+}
+
 uint32_t lb_emul_decode(const uint8_t *cw, uint32_t n_cw, int is_header, uint32_t cr, uint8_t *out, uint32_t cap) {
     uint32_t n = lb::decode_len_bytes(lb::decode_len_words(n_cw, is_header), cr);
     if (n > cap) n = cap;

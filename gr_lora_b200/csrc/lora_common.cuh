@@ -163,12 +163,20 @@ LB_HD float key_mag2(unsigned long long k) {
 // degree-7 minimax P fitted to relative error (1.7e-8 before rounding), then the octant fix-ups: 26 instructions, measured
 // max error 1.8 ulp on 4e6 random points (CUDA documents 2 ulp for atan2f, so the two are interchangeable for parity:
 // both differ from glibc's result in the last bit on a fraction of the samples).  Zero, infinite and NaN inputs follow C99.
-LB_D float lb_atan2f(float y, float x) {
+LB_HD float lb_atan2f(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+#ifdef __CUDA_ARCH__
     float q = __fdiv_rn(mn, mx);
+    const float inf = __int_as_float(0x7f800000);
+    const bool x_neg = __float_as_int(x) < 0;
+#else                                                                    // the host build (tests/test_host_emulation.py): IEEE division as well
+    float q = mn / mx;
+    const float inf = INFINITY;
+    const bool x_neg = signbit(x);
+#endif
     if (mx == 0.0f) q = 0.0f;                                            // atan2(+-0, +-0)
-    if (mx == __int_as_float(0x7f800000)) q = mn == mx ? 1.0f : 0.0f;    // infinite operands
+    if (mx == inf) q = mn == mx ? 1.0f : 0.0f;                           // infinite operands
     const float s = q * q;
     float p = 0.0029206566978245974f;
     p = fmaf(p, s, -0.01636778749525547f);
@@ -180,7 +188,7 @@ LB_D float lb_atan2f(float y, float x) {
     p = fmaf(p, s, -0.33333152532577515f);
     float r = fmaf(q * s, p, q);
     if (ay > ax) r = 1.5707963705062866211f - r;
-    if (__float_as_int(x) < 0) r = 3.1415927410125732422f - r;
+    if (x_neg) r = 3.1415927410125732422f - r;
     const float sum = ax + ay;
     if (sum != sum) return sum;                                          // NaN in, NaN out
     return copysignf(r, y);

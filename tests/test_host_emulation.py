@@ -34,6 +34,7 @@ def emul():
         getattr(L, n).argtypes = [C.c_uint8]
     L.lb_emul_payload_symbols.restype = C.c_int32
     L.lb_emul_payload_symbols.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
+    L.lb_emul_atan2f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     return L
 
 
@@ -180,3 +181,29 @@ def test_k1_rows_emulation_matches_oracle(emul, oracle, sf):
         ob, om = d.demod_fft_batch(x)
         assert np.array_equal(bins, ob)
         np.testing.assert_allclose(mags, om, rtol=2e-6)
+
+
+def test_atan2_of_the_stream_kernels(emul):
+    """lb_atan2f (lora_common.cuh), the arg() of the instantaneous-frequency passes: within 2 ulp of the exact value on
+    2e6 points over all octants and 60 decades of magnitude (measured maximum 1.8), and C99's results for zeros, infinities and NaN.  (The GPU executes the same source with the same IEEE operations.)"""
+    rng = np.random.default_rng(3)
+    n = 2_000_000
+    mag = np.float32(10.0) ** rng.uniform(-30, 30, n).astype(np.float32)
+    x = (rng.standard_normal(n).astype(np.float32) * mag).astype(np.float32)
+    y = (rng.standard_normal(n).astype(np.float32) * mag * np.float32(10.0) ** rng.uniform(-3, 3, n).astype(np.float32)).astype(np.float32)
+    y[np.isinf(y)] = 1.0
+    out = np.empty(n, np.float32)
+    emul.lb_emul_atan2f(y.ctypes.data, x.ctypes.data, out.ctypes.data, n)
+    exact = np.arctan2(y.astype(np.float64), x.astype(np.float64))
+    ulp = np.spacing(np.abs(exact).astype(np.float32)).astype(np.float64)
+    err = np.abs(out.astype(np.float64) - exact) / ulp
+    assert err.max() < 2.0, err.max()
+    assert np.all(np.abs(out) <= np.float32(np.pi))
+    sp_y = np.array([0.0, -0.0, 0.0, -0.0, 1.0, -1.0, 0.0, -0.0, np.inf, -np.inf, np.inf, -np.inf, 1.0, 1.0, np.inf, np.nan, 1.0], np.float32)
+    sp_x = np.array([0.0, 0.0, -0.0, -0.0, 0.0, 0.0, -1.0, -1.0, np.inf, np.inf, -np.inf, -np.inf, np.inf, -np.inf, 1.0, 1.0, np.nan], np.float32)
+    got = np.empty(sp_y.size, np.float32)
+    emul.lb_emul_atan2f(sp_y.ctypes.data, sp_x.ctypes.data, got.ctypes.data, sp_y.size)
+    want = np.arctan2(sp_y.astype(np.float64), sp_x.astype(np.float64)).astype(np.float32)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.allclose(got[ok], want[ok], rtol=0, atol=2.4e-7) and np.array_equal(np.signbit(got[ok]), np.signbit(want[ok]))
