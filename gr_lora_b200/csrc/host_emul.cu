@@ -7,6 +7,7 @@
 #include "k1_sf10.cuh"
 #include "k1_rows.cuh"
 #include "int_chain.cuh"
+#include "tx_channel.cuh"
 
 extern "C" {
 
@@ -51,6 +52,13 @@ int lb_k1_emulate_rows(int sf, const float2 *x, size_t n_symbols, const float2 *
     return 0;
 }
 
+
+// the counter-based generator of the transmitter / channel kernels (tx_channel.cuh), on the host
+void lb_emul_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+    uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+    lb::philox4x32_10(c, key[0], key[1]);
+    for (int i = 0; i < 4; i++) out[i] = c[i];
+}
 
 // the stream kernels' arg() (lora_common.cuh), on the host
 void lb_emul_atan2f(const float *y, const float *x, float *out, size_t n) {

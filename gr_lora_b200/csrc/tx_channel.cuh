@@ -14,22 +14,32 @@
 
 namespace lb {
 #ifdef __CUDACC__
-LB_D void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+LB_HD uint32_t philox_mulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((unsigned long long)a * b) >> 32);
+#endif
+}
+LB_HD void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+    const uint32_t hi0 = philox_mulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = philox_mulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
     const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
     c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
 }
-// four normal deviates for (row, pair index i) under `seed`
-LB_D float4 philox_normal4(unsigned long long seed, unsigned long long row, unsigned long long i) {
-    uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)row, (uint32_t)(row >> 32)};
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+// Philox4x32-10 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3"): c <- ten rounds under key (k0, k1)
+LB_HD void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         philox_round(c, k0, k1);
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
+}
+// four normal deviates for (row, pair index i) under `seed`
+LB_D float4 philox_normal4(unsigned long long seed, unsigned long long row, unsigned long long i) {
+    uint32_t c[4] = {(uint32_t)i, (uint32_t)(i >> 32), (uint32_t)row, (uint32_t)(row >> 32)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
     const float s = 2.3283064365386963e-10f;                    // 2^-32
     const float u0 = ((float)c[0] + 0.5f) * s, u1 = (float)c[1] * s, u2 = ((float)c[2] + 0.5f) * s, u3 = (float)c[3] * s;
     const float r0 = sqrtf(-2.0f * __logf(fminf(u0, 0.99999994f))), r1 = sqrtf(-2.0f * __logf(fminf(u2, 0.99999994f)));

@@ -35,6 +35,7 @@ def emul():
     L.lb_emul_payload_symbols.restype = C.c_int32
     L.lb_emul_payload_symbols.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
     L.lb_emul_atan2f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.lb_emul_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -207,3 +208,34 @@ def test_atan2_of_the_stream_kernels(emul):
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = ~np.isnan(want)
     assert np.allclose(got[ok], want[ok], rtol=0, atol=2.4e-7) and np.array_equal(np.signbit(got[ok]), np.signbit(want[ok]))
+
+
+def _philox4x32_10(ctr, key):
+    """Philox4x32-10 written from the paper (Salmon, Moraes, Dror, Shaw, SC'11), independent of the product source."""
+    c = [int(v) for v in ctr]
+    k = [int(v) for v in key]
+    for _ in range(10):
+        p0 = 0xD2511F53 * c[0]
+        p1 = 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k[0]) & 0xFFFFFFFF, p1 & 0xFFFFFFFF, ((p0 >> 32) ^ c[3] ^ k[1]) & 0xFFFFFFFF, p0 & 0xFFFFFFFF]
+        k = [(k[0] + 0x9E3779B9) & 0xFFFFFFFF, (k[1] + 0xBB67AE85) & 0xFFFFFFFF]
+    return c
+
+
+def test_philox_of_the_tx_kernels(emul):
+    """The noise generator of csrc/tx_channel.cuh is the standard Philox4x32-10: Random123's known answer for the all-zero
+    counter and key, and an independent implementation on random counters / keys."""
+    def product(ctr, key):
+        c = np.array(ctr, np.uint32)
+        k = np.array(key, np.uint32)
+        o = np.empty(4, np.uint32)
+        emul.lb_emul_philox4x32_10(c.ctypes.data, k.ctypes.data, o.ctypes.data)
+        return [int(v) for v in o]
+
+    assert product([0, 0, 0, 0], [0, 0]) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        ctr = rng.integers(0, 1 << 32, 4, dtype=np.uint64)
+        key = rng.integers(0, 1 << 32, 2, dtype=np.uint64)
+        assert product(ctr, key) == _philox4x32_10(ctr, key)
+    assert product([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2) == _philox4x32_10([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2)
