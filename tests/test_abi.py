@@ -79,3 +79,14 @@ def test_documented_defaults_match_the_implementation():
     src = (ROOT / "gr_lora_b200" / "csrc" / "lora_b200.cu").read_text()
     assert "max_frames_per_call;/* per stream (0 = 8)" in hdr
     assert "if (d->cfg.max_frames_per_call == 0) d->cfg.max_frames_per_call = 8;" in src
+
+
+def test_every_abi_entry_point_is_mapped_in_integration_md():
+    """INTEGRATION.md is the map from the reference's interface to the C ABI: every function include/lora_b200.h declares
+    must have a row there."""
+    import re
+    root = Path(__file__).resolve().parent.parent
+    names = sorted(set(re.findall(r"\b(lora_b200_[a-z0-9_]+)\s*\(", (root / "include" / "lora_b200.h").read_text())))
+    doc = (root / "INTEGRATION.md").read_text()
+    missing = [n for n in names if n not in doc]
+    assert len(names) > 40 and not missing, missing
